@@ -1,0 +1,155 @@
+/*
+ * include/gravity_cuda.h -- C ABI of libgravity_cuda, the B200 (sm_100a)
+ * replacement for the all-pairs gravity step of sthaid/proj_entropy.
+ *
+ * The reference has no plugin/FFI seam for this path: the arithmetic is inline
+ * in the worker thread of a static-state translation unit whose only export
+ * is `void sim_gravity(void)` (util.h:42).  This header therefore DEFINES the
+ * seam.  It is cut around the body of `if (local_state == STATE_RUN) {...}`
+ * (sim_gravity.c:1176-1261): the k-loop (:1183-1222), barrier B2 (:1226) and
+ * the NEXT_* -> state copy (:1242-1245) become one call made by worker 0;
+ * `sim.sim_time += DT` (:1255) and the once-per-day PATH sampling
+ * (:1232-1236, :1248-1251, :1258-1260) stay in host C.  INTEGRATION.md shows
+ * the patch a maintainer of the reference would apply.
+ *
+ * Conventions, mirroring the reference:
+ *   - plain C types only; no C++ types or exceptions cross this boundary;
+ *   - every function returns 0 on success and a negative value on failure
+ *     (the `ret = -1` pattern of sim_gravity.c:218,264-268) and never calls
+ *     exit() (unlike FATAL, util.h:236-240); the message, at most 199
+ *     characters so that it fits one error_str row (sim_gravity.c:136), is
+ *     read with gravity_cuda_last_error();
+ *   - all body state is fp64 SI (m, m/s, kg; sim_gravity.c:85-90); the step
+ *     size is an int32 number of seconds like DT (sim_gravity.c:124) and is
+ *     snapshotted per call;
+ *   - G = 6.673E-11 (sim_gravity.c:29), 2-D, no softening; the evaluated body
+ *     is half-drifted, the others are not (sim_gravity.c:1186-1197); self is
+ *     skipped by index (:1191) and exactly coincident pairs are skipped
+ *     (:1199-1201);
+ *   - there is NO CPU fallback: without a usable sm_100 device every entry
+ *     point fails with an error.
+ *
+ * A handle is used by one host thread at a time (in the reference only thread
+ * 0 commits, sim_gravity.c:1229).  Host arrays are borrowed for the duration
+ * of a call; device state is authoritative between upload and download.
+ */
+#ifndef GRAVITY_CUDA_H
+#define GRAVITY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gravity_cuda gravity_cuda_t;
+
+#define GRAVITY_CUDA_G 6.673E-11          /* sim_gravity.c:29 */
+
+/* Which kernel family evaluates sim_gravity.c:1189-1205. */
+#define GRAVITY_CUDA_KERNEL_AUTO    0     /* N <= 1024: STRICT, else TILED       */
+#define GRAVITY_CUDA_KERNEL_TILED   1     /* rsqrt-based, j tiles in shared
+                                             memory, work split over all SMs;
+                                             matches the reference to ~1e-15     */
+#define GRAVITY_CUDA_KERNEL_STRICT  2     /* IEEE sqrt/div, no FMA, j ascending:
+                                             bit-identical to sim_gravity.c      */
+
+#define GRAVITY_CUDA_NCCL_ID_BYTES 128
+
+/* ---- life cycle --------------------------------------------------------- */
+
+/* Single-process handle over devices 0..ngpus-1 of one box (ngpus >= 1).
+ * Replaces worker creation at sim_gravity.c:425-442: the i-bodies that the
+ * reference strides over max_thread pthreads (:1183) are sharded in
+ * contiguous blocks over the GPUs. */
+int gravity_cuda_create(gravity_cuda_t **out, int64_t n, int ngpus);
+
+/* One-process-per-GPU handle (torchrun style): this process is `rank` of
+ * `nranks` and drives CUDA device `device`.  `nccl_id` is the
+ * GRAVITY_CUDA_NCCL_ID_BYTES blob produced by gravity_cuda_nccl_unique_id() on
+ * rank 0 and broadcast by the host; it may be NULL when nranks == 1. */
+int gravity_cuda_nccl_unique_id(void *id_out, size_t id_bytes);
+int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nranks,
+                             int device, const void *nccl_id, size_t id_bytes);
+
+/* Replaces sim_gravity_terminate's worker join (sim_gravity.c:487-502). */
+void gravity_cuda_destroy(gravity_cuda_t *h);
+
+/* Message of the last failure on this handle; h == NULL returns the message of
+ * the last failed create on the calling thread. */
+const char *gravity_cuda_last_error(const gravity_cuda_t *h);
+
+/* Options: "kernel" (GRAVITY_CUDA_KERNEL_*), "threads" (CTA size of the tiled
+ * kernel: 128|256), "bodies_per_thread" (1|2|4), "ctas_per_sm" (1..8),
+ * "overlap" (0|1: start the local j-shard while the all-gather is in flight).
+ * Must be set before the first step/accel after create. */
+int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value);
+
+/* ---- state -------------------------------------------------------------- */
+
+/* Host SoA, n doubles each: MASS, X, Y, VX, VY of object_t
+ * (sim_gravity.c:85-90).  In rank mode every rank passes the full arrays. */
+int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x,
+                        const double *y, const double *vx, const double *vy);
+
+/* Any pointer may be NULL.  Full-length arrays are returned on every rank. */
+int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, double *vy);
+
+/* ---- the hot path ------------------------------------------------------- */
+
+/* nsteps iterations of sim_gravity.c:1183-1222 + the commit at :1242-1245.
+ * Returns after the device has finished.  The caller advances sim_time by
+ * dt*nsteps (:1255).  To keep PATH sampling identical to :1234-1251 the host
+ * passes nsteps only up to the next day boundary. */
+int gravity_cuda_step(gravity_cuda_t *h, int32_t dt, int64_t nsteps);
+
+/* Same, but only enqueues the work; gravity_cuda_sync() waits for it. */
+int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps);
+int gravity_cuda_sync(gravity_cuda_t *h);
+
+/* AX, AY exactly as at sim_gravity.c:1207-1208 for the current state (n
+ * doubles each); the state is not advanced. */
+int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay);
+
+/* AoS convenience for the reference host: gathers MASS,X,Y,VX,VY from n
+ * object_t-like records reached through objects[i] by byte offset (X@32, Y@40,
+ * VX@48, VY@56, MASS@64 in sim_gravity.c:83-105), steps, and scatters
+ * X,Y,VX,VY back, so the shim never needs the 1.5 MB struct definition. */
+int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n,
+                              size_t off_x, size_t off_y, size_t off_vx, size_t off_vy,
+                              size_t off_mass, int32_t dt, int64_t nsteps);
+
+/* ---- diagnostics and measurement ---------------------------------------- */
+
+/* kinetic = 1/2 sum m|v|^2, potential = -sum_{i<j} G m_i m_j / r_ij (r == 0
+ * skipped) of the current, un-drifted state.  The reference computes neither;
+ * the definitions follow the equations at sim_gravity.c:1145-1174. */
+int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential);
+
+/* CUDA-event timer on the handle's compute stream(s): start/stop bracket any
+ * number of step_async calls; *ms is the maximum over the handle's devices. */
+int gravity_cuda_timer_start(gravity_cuda_t *h);
+int gravity_cuda_timer_stop(gravity_cuda_t *h, double *ms);
+
+/* Kernels launched by this handle since create (all devices). */
+int gravity_cuda_launch_count(const gravity_cuda_t *h, int64_t *launches);
+
+/* Device time (ms) of the dominant kernel (the tiled pair-accumulation kernel,
+ * or the strict one in STRICT mode) summed over the launches since the last
+ * timer_start, measured with CUDA events around each launch, and how many
+ * launches that was.  Valid after timer_stop. */
+int gravity_cuda_kernel_time(gravity_cuda_t *h, double *ms_total, int64_t *launches);
+
+/* Dependent-free DFMA microbenchmark on `device`: measured FP64 FMA-pipe
+ * throughput in TFLOP/s (2 flops per lane-FMA) and the SM clock it ran at
+ * (MHz, from the device's clock64 against the event time). */
+int gravity_cuda_fp64_peak(int device, double *tflops, double *sm_mhz);
+
+/* Number of usable sm_100 devices, or a negative value. */
+int gravity_cuda_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

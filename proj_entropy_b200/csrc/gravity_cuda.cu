@@ -1,0 +1,956 @@
+// gravity_cuda.cu -- host side of libgravity_cuda: the C ABI declared in
+// include/gravity_cuda.h, device memory, streams, NCCL, launch planning.
+//
+// There is no CPU code path for the arithmetic in this file: every entry point
+// that computes anything launches the sm_100a kernels of gravity_kernels.cuh
+// and fails with an error when no such device is usable.
+#include "gravity_cuda.h"
+#include "gravity_kernels.cuh"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace gravity;
+
+namespace {
+
+thread_local char g_create_error[200] = "";
+
+struct DeviceCtx {
+    int rank   = 0;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    ncclComm_t   comm = nullptr;
+    cudaEvent_t  ev_start = nullptr, ev_stop = nullptr, ev_commit = nullptr, ev_gather = nullptr;
+
+    double2 *pos[2] = {nullptr, nullptr};
+    double  *mass = nullptr;
+    double2 *vel = nullptr;
+    double2 *accel = nullptr;
+    double  *kin = nullptr, *pot = nullptr;
+    double2 *partial = nullptr;
+    Segment *seg = nullptr;
+    int32_t *cta_seg_begin = nullptr;
+    int32_t *iblock_seg_begin = nullptr;
+
+    int64_t i0 = 0;          // global index of local body 0
+    int64_t n_local = 0;     // real bodies in this shard
+
+    // launch plan of the tiled kernel: up to two phases (local j-shard first,
+    // then the rest) when overlap is on, otherwise one.
+    struct Phase { int n_cta = 0; int cta_seg_offset = 0; };
+    Phase phase[2];
+    int n_phase = 0;
+    int n_iblock = 0;
+    int n_seg = 0;
+    int threads = 0, bpt = 0, minb = 0;
+
+    // per-launch kernel timing (device 0 of the handle only)
+    std::vector<cudaEvent_t> kev;
+    size_t kev_used = 0;
+};
+
+}  // namespace
+
+struct gravity_cuda {
+    int64_t n = 0, chunk = 0, npad = 0;
+    int nranks = 1;
+    bool single_process = true;
+    std::vector<DeviceCtx> ctx;      // local devices (all of them in single-process mode)
+    int cur = 0;                     // which pos[] holds time t
+    bool uploaded = false, planned = false;
+    int opt_kernel = GRAVITY_CUDA_KERNEL_AUTO;
+    int opt_threads = 256, opt_bpt = 2, opt_ctas_per_sm = 2, opt_overlap = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    int64_t hot_launches = 0;
+    std::vector<double> host_stage;  // staging for AoS adapter / download
+    char err[200] = "";
+};
+
+namespace {
+
+int fail(gravity_cuda_t *h, const char *fmt, ...)
+{
+    char *dst = h ? h->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 200, fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+#define CUDA_TRY(h, expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail((h), "CUDA %s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NCCL_TRY(h, expr)                                                                     \
+    do {                                                                                      \
+        ncclResult_t r_ = (expr);                                                             \
+        if (r_ != ncclSuccess)                                                                \
+            return fail((h), "NCCL %s: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+int check_device(gravity_cuda_t *h, int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(h, "no CUDA device: %s (libgravity_cuda has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(h, "device %d out of range (have %d)", device, count);
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(h, "device %d is sm_%d%d; libgravity_cuda is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    return 0;
+}
+
+int effective_kernel(const gravity_cuda_t *h)
+{
+    if (h->opt_kernel != GRAVITY_CUDA_KERNEL_AUTO) return h->opt_kernel;
+    return h->n <= kSmallMax ? GRAVITY_CUDA_KERNEL_STRICT : GRAVITY_CUDA_KERNEL_TILED;
+}
+
+// ---- kernel dispatch over (threads, bodies per thread) ----------------------
+
+typedef void (*accum_kernel_t)(const AccumParams);
+
+template <int T, int R>
+accum_kernel_t accum_for_minb(int minb)
+{
+    switch (minb) {
+    case 1: return k_tiled_accumulate<T, R, 1>;
+    case 2: return k_tiled_accumulate<T, R, 2>;
+    case 3: return k_tiled_accumulate<T, R, 3>;
+    default: return k_tiled_accumulate<T, R, 4>;
+    }
+}
+
+accum_kernel_t pick_accum(int threads, int bpt, int minb)
+{
+    if (threads == 128) {
+        if (bpt == 1) return accum_for_minb<128, 1>(minb);
+        if (bpt == 2) return accum_for_minb<128, 2>(minb);
+        if (bpt == 4) return accum_for_minb<128, 4>(minb);
+    } else if (threads == 256) {
+        if (bpt == 1) return accum_for_minb<256, 1>(minb);
+        if (bpt == 2) return accum_for_minb<256, 2>(minb);
+        if (bpt == 4) return accum_for_minb<256, 4>(minb);
+    }
+    return nullptr;
+}
+
+// ---- launch plan -------------------------------------------------------------
+
+// Flatten (i-block, j-tile) units i-block-major over the tile list `tiles`,
+// cut them into n_cta equal contiguous runs, and append the resulting segments.
+void plan_phase(const std::vector<int> &tile_runs /* pairs begin,end */, int n_iblock, int max_cta,
+                std::vector<Segment> &segs, std::vector<int32_t> &cta_begin, DeviceCtx::Phase &ph)
+{
+    int64_t tiles_per_block = 0;
+    for (size_t k = 0; k + 1 < tile_runs.size(); k += 2) tiles_per_block += tile_runs[k + 1] - tile_runs[k];
+    const int64_t W = (int64_t)n_iblock * tiles_per_block;
+    ph.cta_seg_offset = (int)cta_begin.size();
+    if (W == 0) {
+        ph.n_cta = 0;
+        cta_begin.push_back((int32_t)segs.size());
+        return;
+    }
+    const int C = (int)std::min<int64_t>(W, max_cta);
+    ph.n_cta = C;
+    for (int c = 0; c < C; ++c) {
+        int64_t u = (W * c) / C;
+        const int64_t u1 = (W * (c + 1)) / C;
+        cta_begin.push_back((int32_t)segs.size());
+        while (u < u1) {
+            const int ib = (int)(u / tiles_per_block);
+            int64_t off = u % tiles_per_block;       // offset inside this block's tile list
+            // locate the run containing `off`
+            size_t k = 0;
+            while (off >= tile_runs[k + 1] - tile_runs[k]) {
+                off -= tile_runs[k + 1] - tile_runs[k];
+                k += 2;
+            }
+            const int t0 = tile_runs[k] + (int)off;
+            const int64_t room = std::min<int64_t>(tile_runs[k + 1] - t0, u1 - u);
+            Segment s;
+            s.iblock = ib;
+            s.tile_begin = t0;
+            s.tile_end = t0 + (int)room;
+            s.slot = 0;
+            segs.push_back(s);
+            u += room;
+        }
+    }
+    cta_begin.push_back((int32_t)segs.size());
+}
+
+int build_plan(gravity_cuda_t *h)
+{
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        c.threads = h->opt_threads;
+        c.bpt = h->opt_bpt;
+        accum_kernel_t probe = pick_accum(c.threads, c.bpt, h->opt_ctas_per_sm);
+        if (!probe) return fail(h, "unsupported tiled kernel shape threads=%d bodies_per_thread=%d", c.threads, c.bpt);
+        int occ = 0;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe, c.threads, 0));
+        if (occ < 1) return fail(h, "tiled kernel does not fit on an SM");
+        c.minb = std::min(occ, h->opt_ctas_per_sm);
+        const int max_cta = c.num_sms * c.minb;
+
+        const int IB = c.threads * c.bpt;
+        c.n_iblock = (int)((c.n_local + IB - 1) / IB);
+        const int n_tile = (int)((h->n + kTile - 1) / kTile);
+
+        std::vector<Segment> segs;
+        std::vector<int32_t> cta_begin;
+        c.n_phase = 0;
+        if (h->opt_overlap && h->nranks > 1) {
+            // phase 0: tiles inside this rank's own shard (already local when the
+            // step starts); phase 1: everything else (needs the all-gather).
+            const int lt0 = (int)(c.i0 / kTile);
+            const int lt1 = (int)std::min<int64_t>(n_tile, (c.i0 + h->chunk) / kTile);
+            std::vector<int> local_runs = {lt0, std::max(lt0, lt1)};
+            std::vector<int> remote_runs;
+            if (lt0 > 0) { remote_runs.push_back(0); remote_runs.push_back(lt0); }
+            if (lt1 < n_tile) { remote_runs.push_back(std::max(lt0, lt1)); remote_runs.push_back(n_tile); }
+            if (remote_runs.empty()) { remote_runs.push_back(0); remote_runs.push_back(0); }
+            plan_phase(local_runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
+            plan_phase(remote_runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[1]);
+            c.n_phase = 2;
+        } else {
+            std::vector<int> runs = {0, n_tile};
+            plan_phase(runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
+            c.n_phase = 1;
+        }
+        c.n_seg = (int)segs.size();
+
+        // The commit kernel adds up the partial rows of one i-block in a fixed
+        // order.  Give every segment a partial row ("slot") such that the rows
+        // of one i-block are contiguous and ordered by (phase, CTA): a stable
+        // sort of the segment list on iblock.
+        std::vector<int> order(segs.size());
+        for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int a, int b) { return segs[a].iblock < segs[b].iblock; });
+        std::vector<int32_t> slot_of(segs.size());
+        for (size_t k = 0; k < order.size(); ++k) slot_of[order[k]] = (int32_t)k;
+        for (size_t k = 0; k < segs.size(); ++k) segs[k].slot = slot_of[k];
+        std::vector<int32_t> ib_begin(c.n_iblock + 1, 0);
+        for (const Segment &s : segs) ib_begin[s.iblock + 1]++;
+        for (int b = 0; b < c.n_iblock; ++b) ib_begin[b + 1] += ib_begin[b];
+
+        cudaFree(c.seg); cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin); cudaFree(c.partial);
+        c.seg = nullptr; c.cta_seg_begin = nullptr; c.iblock_seg_begin = nullptr; c.partial = nullptr;
+        CUDA_TRY(h, cudaMalloc(&c.seg, sizeof(Segment) * std::max<size_t>(1, segs.size())));
+        CUDA_TRY(h, cudaMalloc(&c.cta_seg_begin, sizeof(int32_t) * std::max<size_t>(1, cta_begin.size())));
+        CUDA_TRY(h, cudaMalloc(&c.iblock_seg_begin, sizeof(int32_t) * ib_begin.size()));
+        CUDA_TRY(h, cudaMalloc(&c.partial, sizeof(double2) * std::max<size_t>(1, segs.size()) * IB));
+        CUDA_TRY(h, cudaMemcpy(c.seg, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(c.cta_seg_begin, cta_begin.data(), sizeof(int32_t) * cta_begin.size(),
+                               cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(c.iblock_seg_begin, ib_begin.data(), sizeof(int32_t) * ib_begin.size(),
+                               cudaMemcpyHostToDevice));
+    }
+    h->planned = true;
+    return 0;
+}
+
+// ---- timing helpers -------------------------------------------------------------
+
+void hot_event(gravity_cuda_t *h, DeviceCtx &c)
+{
+    if (!h->timing || &c != &h->ctx[0]) return;
+    if (c.kev_used >= 8192) return;
+    if (c.kev_used == c.kev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c.kev.push_back(e);
+    }
+    cudaEventRecord(c.kev[c.kev_used++], c.stream);
+}
+
+// ---- one step on every local device -----------------------------------------------
+
+int launch_tiled_phase(gravity_cuda_t *h, DeviceCtx &c, int phase, double dt)
+{
+    const DeviceCtx::Phase &ph = c.phase[phase];
+    if (ph.n_cta == 0) return 0;
+    AccumParams P;
+    P.pos = c.pos[h->cur];
+    P.mass = c.mass;
+    P.vel = c.vel;
+    P.partial = c.partial;
+    P.seg = c.seg;
+    P.cta_seg_begin = c.cta_seg_begin + ph.cta_seg_offset;
+    P.i_global0 = c.i0;
+    P.n_local = c.n_local;
+    P.dt = dt;
+    accum_kernel_t k = pick_accum(c.threads, c.bpt, c.minb);
+    hot_event(h, c);
+    k<<<ph.n_cta, c.threads, 0, c.stream>>>(P);
+    hot_event(h, c);
+    h->launches++;
+    if (&c == &h->ctx[0]) h->hot_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+CommitParams commit_params(gravity_cuda_t *h, DeviceCtx &c, double dt, bool export_accel)
+{
+    CommitParams P;
+    P.pos_cur = c.pos[h->cur];
+    P.pos_next = c.pos[h->cur ^ 1];
+    P.vel = c.vel;
+    P.mass = c.mass;
+    P.partial = c.partial;
+    P.iblock_seg_begin = c.iblock_seg_begin;
+    P.accel_out = c.accel;
+    P.n = h->n;
+    P.i_global0 = c.i0;
+    P.n_local = c.n_local;
+    P.iblock_size = c.threads * c.bpt;
+    P.export_accel = export_accel ? 1 : 0;
+    P.dt = dt;
+    return P;
+}
+
+// Evaluate sim_gravity.c:1183-1222 once on all local devices, either advancing
+// the state (export_accel == false) or writing AX,AY into ctx.accel.
+int enqueue_evaluation(gravity_cuda_t *h, double dt, bool export_accel, bool gather_after)
+{
+    const int kernel = effective_kernel(h);
+    if (kernel == GRAVITY_CUDA_KERNEL_TILED && !h->planned) {
+        if (build_plan(h) != 0) return -1;
+    }
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        if (c.n_local == 0) continue;
+        if (kernel == GRAVITY_CUDA_KERNEL_TILED) {
+            if (launch_tiled_phase(h, c, 0, dt) != 0) return -1;
+            if (c.n_phase == 2) {
+                // remote tiles need the previous step's all-gather
+                CUDA_TRY(h, cudaStreamWaitEvent(c.stream, c.ev_gather, 0));
+                if (launch_tiled_phase(h, c, 1, dt) != 0) return -1;
+            }
+            const CommitParams P = commit_params(h, c, dt, export_accel);
+            const int grid = (int)((c.n_local + kCommitThreads - 1) / kCommitThreads);
+            k_commit_partials<<<grid, kCommitThreads, 0, c.stream>>>(P);
+            h->launches++;
+        } else {
+            const CommitParams P = commit_params(h, c, dt, export_accel);
+            const int grid = (int)((c.n_local + kStrictThreads - 1) / kStrictThreads);
+            hot_event(h, c);
+            k_strict_rows<<<grid, kStrictThreads, 0, c.stream>>>(P);
+            hot_event(h, c);
+            h->launches++;
+            if (&c == &h->ctx[0]) h->hot_launches++;
+        }
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    if (!export_accel && gather_after && h->nranks > 1) {
+        // barrier B2 + the NEXT_* -> state copy (sim_gravity.c:1226, :1242-1245)
+        // become one in-place all-gather of the new positions.
+        const bool two_stream = h->opt_overlap != 0;
+        if (two_stream) {
+            for (DeviceCtx &c : h->ctx) {
+                CUDA_TRY(h, cudaSetDevice(c.device));
+                CUDA_TRY(h, cudaEventRecord(c.ev_commit, c.stream));
+                CUDA_TRY(h, cudaStreamWaitEvent(c.comm_stream, c.ev_commit, 0));
+            }
+        }
+        NCCL_TRY(h, ncclGroupStart());
+        for (DeviceCtx &c : h->ctx) {
+            double2 *next = c.pos[h->cur ^ 1];
+            NCCL_TRY(h, ncclAllGather(next + c.i0, next, (size_t)h->chunk * 2, ncclDouble, c.comm,
+                                      two_stream ? c.comm_stream : c.stream));
+        }
+        NCCL_TRY(h, ncclGroupEnd());
+        if (two_stream) {
+            for (DeviceCtx &c : h->ctx) {
+                CUDA_TRY(h, cudaSetDevice(c.device));
+                CUDA_TRY(h, cudaEventRecord(c.ev_gather, c.comm_stream));
+            }
+        }
+    }
+    if (!export_accel) h->cur ^= 1;
+    return 0;
+}
+
+int sync_all(gravity_cuda_t *h)
+{
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+        CUDA_TRY(h, cudaStreamSynchronize(c.comm_stream));
+    }
+    return 0;
+}
+
+// with overlap the compute stream must not run ahead of the gather when the
+// caller reads positions or leaves the step loop
+int join_comm(gravity_cuda_t *h)
+{
+    if (!(h->opt_overlap && h->nranks > 1)) return 0;
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaStreamWaitEvent(c.stream, c.ev_gather, 0));
+    }
+    return 0;
+}
+
+int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
+{
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreate(&c.ev_start));
+    CUDA_TRY(h, cudaEventCreate(&c.ev_stop));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&c.ev_commit, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&c.ev_gather, cudaEventDisableTiming));
+    c.i0 = (int64_t)c.rank * h->chunk;
+    c.n_local = std::max<int64_t>(0, std::min<int64_t>(h->chunk, h->n - c.i0));
+    CUDA_TRY(h, cudaMalloc(&c.pos[0], sizeof(double2) * h->npad));
+    CUDA_TRY(h, cudaMalloc(&c.pos[1], sizeof(double2) * h->npad));
+    CUDA_TRY(h, cudaMalloc(&c.mass, sizeof(double) * h->npad));
+    CUDA_TRY(h, cudaMalloc(&c.vel, sizeof(double2) * h->chunk));
+    CUDA_TRY(h, cudaMalloc(&c.accel, sizeof(double2) * h->chunk));
+    CUDA_TRY(h, cudaMalloc(&c.kin, sizeof(double) * h->chunk));
+    CUDA_TRY(h, cudaMalloc(&c.pot, sizeof(double) * h->chunk));
+    CUDA_TRY(h, cudaMemsetAsync(c.vel, 0, sizeof(double2) * h->chunk, c.stream));
+    const int64_t npadding = h->npad - h->n;
+    if (npadding > 0) {
+        k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(c.pos[0], c.pos[1], c.mass, h->n, h->npad);
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    CUDA_TRY(h, cudaEventRecord(c.ev_gather, c.stream));
+    CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+void set_geometry(gravity_cuda_t *h, int64_t n, int nranks)
+{
+    h->n = n;
+    h->nranks = nranks;
+    const int64_t per = (n + nranks - 1) / nranks;
+    h->chunk = ((per + kTile - 1) / kTile) * kTile;      // shards are whole j-tiles
+    if (h->chunk == 0) h->chunk = kTile;
+    h->npad = h->chunk * nranks;
+}
+
+}  // namespace
+
+// ============================================================================
+// C ABI
+// ============================================================================
+
+extern "C" {
+
+int gravity_cuda_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return -1;
+    int usable = 0;
+    for (int d = 0; d < count; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) usable++;
+    }
+    return usable;
+}
+
+const char *gravity_cuda_last_error(const gravity_cuda_t *h) { return h ? h->err : g_create_error; }
+
+int gravity_cuda_nccl_unique_id(void *id_out, size_t id_bytes)
+{
+    if (!id_out || id_bytes < sizeof(ncclUniqueId)) return fail(nullptr, "nccl id buffer too small");
+    ncclUniqueId id;
+    NCCL_TRY(nullptr, ncclGetUniqueId(&id));
+    memset(id_out, 0, id_bytes);
+    memcpy(id_out, &id, sizeof(id));
+    return 0;
+}
+
+static int create_common(gravity_cuda_t **out, int64_t n, int nranks, bool single_process,
+                         int rank, int device, const void *nccl_id, size_t id_bytes)
+{
+    if (!out) return fail(nullptr, "out is NULL");
+    *out = nullptr;
+    if (n < 1) return fail(nullptr, "n must be >= 1 (got %lld)", (long long)n);
+    if (nranks < 1 || nranks > 64) return fail(nullptr, "number of GPUs must be 1..64 (got %d)", nranks);
+    gravity_cuda_t *h = new (std::nothrow) gravity_cuda();
+    if (!h) return fail(nullptr, "out of host memory");
+    h->single_process = single_process;
+    set_geometry(h, n, nranks);
+
+    auto bail = [&](void) {
+        snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+        gravity_cuda_destroy(h);
+        return -1;
+    };
+
+    if (single_process) {
+        h->ctx.resize(nranks);
+        for (int r = 0; r < nranks; ++r) {
+            h->ctx[r].rank = r;
+            h->ctx[r].device = r;
+            if (check_device(h, r) != 0) return bail();
+        }
+    } else {
+        h->ctx.resize(1);
+        h->ctx[0].rank = rank;
+        h->ctx[0].device = device;
+        if (check_device(h, device) != 0) return bail();
+    }
+    for (DeviceCtx &c : h->ctx) {
+        if (init_ctx(h, c) != 0) return bail();
+    }
+    if (nranks > 1) {
+        if (single_process) {
+            std::vector<ncclComm_t> comms(nranks);
+            std::vector<int> devs(nranks);
+            for (int r = 0; r < nranks; ++r) devs[r] = r;
+            ncclResult_t r_ = ncclCommInitAll(comms.data(), nranks, devs.data());
+            if (r_ != ncclSuccess) {
+                fail(h, "NCCL ncclCommInitAll: %s", ncclGetErrorString(r_));
+                return bail();
+            }
+            for (int r = 0; r < nranks; ++r) h->ctx[r].comm = comms[r];
+        } else {
+            if (!nccl_id || id_bytes < sizeof(ncclUniqueId)) {
+                fail(h, "rank mode with nranks > 1 needs the NCCL unique id");
+                return bail();
+            }
+            ncclUniqueId id;
+            memcpy(&id, nccl_id, sizeof(id));
+            cudaSetDevice(device);
+            ncclResult_t r_ = ncclCommInitRank(&h->ctx[0].comm, nranks, id, rank);
+            if (r_ != ncclSuccess) {
+                fail(h, "NCCL ncclCommInitRank: %s", ncclGetErrorString(r_));
+                return bail();
+            }
+        }
+    }
+    *out = h;
+    return 0;
+}
+
+int gravity_cuda_create(gravity_cuda_t **out, int64_t n, int ngpus)
+{
+    return create_common(out, n, ngpus, true, 0, 0, nullptr, 0);
+}
+
+int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nranks, int device,
+                             const void *nccl_id, size_t id_bytes)
+{
+    if (rank < 0 || rank >= nranks) return fail(nullptr, "rank %d out of range 0..%d", rank, nranks - 1);
+    return create_common(out, n, nranks, false, rank, device, nccl_id, id_bytes);
+}
+
+void gravity_cuda_destroy(gravity_cuda_t *h)
+{
+    if (!h) return;
+    for (DeviceCtx &c : h->ctx) {
+        cudaSetDevice(c.device);
+        if (c.stream) cudaStreamSynchronize(c.stream);
+        if (c.comm_stream) cudaStreamSynchronize(c.comm_stream);
+        if (c.comm) ncclCommDestroy(c.comm);
+        cudaFree(c.pos[0]); cudaFree(c.pos[1]); cudaFree(c.mass); cudaFree(c.vel); cudaFree(c.accel);
+        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.partial); cudaFree(c.seg);
+        cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin);
+        for (cudaEvent_t e : c.kev) cudaEventDestroy(e);
+        if (c.ev_start) cudaEventDestroy(c.ev_start);
+        if (c.ev_stop) cudaEventDestroy(c.ev_stop);
+        if (c.ev_commit) cudaEventDestroy(c.ev_commit);
+        if (c.ev_gather) cudaEventDestroy(c.ev_gather);
+        if (c.stream) cudaStreamDestroy(c.stream);
+        if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
+    }
+    delete h;
+}
+
+int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
+{
+    if (!h || !key) return fail(h, "set_option: NULL argument");
+    if (!strcmp(key, "kernel")) {
+        if (value < 0 || value > 2) return fail(h, "kernel must be 0 (auto), 1 (tiled) or 2 (strict)");
+        h->opt_kernel = (int)value;
+    } else if (!strcmp(key, "threads")) {
+        if (value != 128 && value != 256) return fail(h, "threads must be 128 or 256");
+        h->opt_threads = (int)value;
+    } else if (!strcmp(key, "bodies_per_thread")) {
+        if (value != 1 && value != 2 && value != 4) return fail(h, "bodies_per_thread must be 1, 2 or 4");
+        h->opt_bpt = (int)value;
+    } else if (!strcmp(key, "ctas_per_sm")) {
+        if (value < 1 || value > 8) return fail(h, "ctas_per_sm must be 1..8");
+        h->opt_ctas_per_sm = (int)value;
+    } else if (!strcmp(key, "overlap")) {
+        h->opt_overlap = value ? 1 : 0;
+    } else {
+        return fail(h, "unknown option '%s'", key);
+    }
+    h->planned = false;
+    return 0;
+}
+
+int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, const double *y,
+                        const double *vx, const double *vy)
+{
+    if (!h) return fail(nullptr, "upload: NULL handle");
+    if (!mass || !x || !y || !vx || !vy) return fail(h, "upload: NULL array");
+    if (sync_all(h) != 0) return -1;
+    const int64_t n = h->n;
+    std::vector<double> &st = h->host_stage;
+    st.resize((size_t)4 * n);
+    double *pxy = st.data();            // interleaved {x,y}
+    double *vxy = st.data() + 2 * n;    // interleaved {vx,vy}
+    for (int64_t i = 0; i < n; ++i) {
+        pxy[2 * i] = x[i];
+        pxy[2 * i + 1] = y[i];
+        vxy[2 * i] = vx[i];
+        vxy[2 * i + 1] = vy[i];
+    }
+    h->cur = 0;
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaMemcpyAsync(c.pos[0], pxy, sizeof(double2) * n, cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(h, cudaMemcpyAsync(c.mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+        if (c.n_local > 0)
+            CUDA_TRY(h, cudaMemcpyAsync(c.vel, vxy + 2 * c.i0, sizeof(double2) * c.n_local,
+                                        cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(h, cudaEventRecord(c.ev_gather, c.stream));
+    }
+    if (sync_all(h) != 0) return -1;
+    h->uploaded = true;
+    return 0;
+}
+
+int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, double *vy)
+{
+    if (!h) return fail(nullptr, "download: NULL handle");
+    if (!h->uploaded) return fail(h, "download before upload");
+    if (join_comm(h) != 0 || sync_all(h) != 0) return -1;
+    const int64_t n = h->n;
+    std::vector<double> &st = h->host_stage;
+    st.resize((size_t)4 * n);
+    double *pxy = st.data();
+    double *vxy = st.data() + 2 * n;
+    if (x || y) {
+        DeviceCtx &c = h->ctx[0];
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaMemcpy(pxy, c.pos[h->cur], sizeof(double2) * n, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; ++i) {
+            if (x) x[i] = pxy[2 * i];
+            if (y) y[i] = pxy[2 * i + 1];
+        }
+    }
+    if (vx || vy) {
+        if (h->single_process) {
+            for (DeviceCtx &c : h->ctx) {
+                if (c.n_local == 0) continue;
+                CUDA_TRY(h, cudaSetDevice(c.device));
+                CUDA_TRY(h, cudaMemcpy(vxy + 2 * c.i0, c.vel, sizeof(double2) * c.n_local, cudaMemcpyDeviceToHost));
+            }
+        } else if (h->nranks == 1) {
+            DeviceCtx &c = h->ctx[0];
+            CUDA_TRY(h, cudaMemcpy(vxy, c.vel, sizeof(double2) * c.n_local, cudaMemcpyDeviceToHost));
+        } else {
+            // rank mode: gather the velocity shards through the spare position buffer
+            DeviceCtx &c = h->ctx[0];
+            CUDA_TRY(h, cudaSetDevice(c.device));
+            double2 *tmp = c.pos[h->cur ^ 1];
+            CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.vel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
+            NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
+            CUDA_TRY(h, cudaMemcpyAsync(vxy, tmp, sizeof(double2) * n, cudaMemcpyDeviceToHost, c.stream));
+            // restore the padding the gather overwrote with velocity padding (zeros)
+            const int64_t npadding = h->npad - h->n;
+            if (npadding > 0) {
+                k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(tmp, tmp, c.mass, h->n, h->npad);
+            }
+            CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            if (vx) vx[i] = vxy[2 * i];
+            if (vy) vy[i] = vxy[2 * i + 1];
+        }
+    }
+    return 0;
+}
+
+int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
+{
+    if (!h) return fail(nullptr, "step: NULL handle");
+    if (!h->uploaded) return fail(h, "step before upload");
+    if (nsteps < 0) return fail(h, "nsteps must be >= 0");
+    if (nsteps == 0) return 0;
+    const double dtd = (double)dt;
+    const int kernel = effective_kernel(h);
+    if (kernel == GRAVITY_CUDA_KERNEL_STRICT && h->nranks == 1 && h->n <= kSmallMax) {
+        // the whole batch in one single-CTA launch
+        DeviceCtx &c = h->ctx[0];
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        const int threads = (int)(((h->n + 31) / 32) * 32);
+        hot_event(h, c);
+        k_small_strict_steps<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
+                                                          (long long)nsteps);
+        hot_event(h, c);
+        h->launches++;
+        h->hot_launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
+    for (int64_t s = 0; s < nsteps; ++s) {
+        if (enqueue_evaluation(h, dtd, false, true) != 0) return -1;
+    }
+    return 0;
+}
+
+int gravity_cuda_sync(gravity_cuda_t *h)
+{
+    if (!h) return fail(nullptr, "sync: NULL handle");
+    if (join_comm(h) != 0) return -1;
+    return sync_all(h);
+}
+
+int gravity_cuda_step(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
+{
+    if (gravity_cuda_step_async(h, dt, nsteps) != 0) return -1;
+    return gravity_cuda_sync(h);
+}
+
+int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay)
+{
+    if (!h) return fail(nullptr, "accel: NULL handle");
+    if (!h->uploaded) return fail(h, "accel before upload");
+    if (!ax || !ay) return fail(h, "accel: NULL array");
+    if (join_comm(h) != 0) return -1;
+    if (enqueue_evaluation(h, (double)dt, true, false) != 0) return -1;
+    if (sync_all(h) != 0) return -1;
+    const int64_t n = h->n;
+    std::vector<double> &st = h->host_stage;
+    st.resize((size_t)4 * n);
+    double *axy = st.data();
+    if (h->single_process || h->nranks == 1) {
+        for (DeviceCtx &c : h->ctx) {
+            if (c.n_local == 0) continue;
+            CUDA_TRY(h, cudaSetDevice(c.device));
+            CUDA_TRY(h, cudaMemcpy(axy + 2 * c.i0, c.accel, sizeof(double2) * c.n_local, cudaMemcpyDeviceToHost));
+        }
+    } else {
+        DeviceCtx &c = h->ctx[0];
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        double2 *tmp = c.pos[h->cur ^ 1];
+        CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.accel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
+        NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
+        CUDA_TRY(h, cudaMemcpyAsync(axy, tmp, sizeof(double2) * n, cudaMemcpyDeviceToHost, c.stream));
+        const int64_t npadding = h->npad - h->n;
+        if (npadding > 0) {
+            k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(tmp, tmp, c.mass, h->n, h->npad);
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        ax[i] = axy[2 * i];
+        ay[i] = axy[2 * i + 1];
+    }
+    return 0;
+}
+
+int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size_t off_x, size_t off_y,
+                              size_t off_vx, size_t off_vy, size_t off_mass, int32_t dt, int64_t nsteps)
+{
+    if (!h) return fail(nullptr, "step_objects: NULL handle");
+    if (!objects) return fail(h, "step_objects: NULL objects");
+    if (n != h->n) return fail(h, "step_objects: n=%lld but the handle was created for %lld", (long long)n,
+                               (long long)h->n);
+    std::vector<double> soa((size_t)5 * n);
+    double *m = soa.data(), *x = m + n, *y = x + n, *vx = y + n, *vy = vx + n;
+    for (int64_t i = 0; i < n; ++i) {
+        const char *o = static_cast<const char *>(objects[i]);
+        if (!o) return fail(h, "step_objects: objects[%lld] is NULL", (long long)i);
+        memcpy(&m[i], o + off_mass, sizeof(double));
+        memcpy(&x[i], o + off_x, sizeof(double));
+        memcpy(&y[i], o + off_y, sizeof(double));
+        memcpy(&vx[i], o + off_vx, sizeof(double));
+        memcpy(&vy[i], o + off_vy, sizeof(double));
+    }
+    if (gravity_cuda_upload(h, m, x, y, vx, vy) != 0) return -1;
+    if (gravity_cuda_step(h, dt, nsteps) != 0) return -1;
+    if (gravity_cuda_download(h, x, y, vx, vy) != 0) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        char *o = static_cast<char *>(objects[i]);
+        memcpy(o + off_x, &x[i], sizeof(double));
+        memcpy(o + off_y, &y[i], sizeof(double));
+        memcpy(o + off_vx, &vx[i], sizeof(double));
+        memcpy(o + off_vy, &vy[i], sizeof(double));
+    }
+    return 0;
+}
+
+int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential)
+{
+    if (!h) return fail(nullptr, "energy: NULL handle");
+    if (!h->uploaded) return fail(h, "energy before upload");
+    if (join_comm(h) != 0) return -1;
+    long double ke = 0, pe = 0;
+    std::vector<double> buf;
+    for (DeviceCtx &c : h->ctx) {
+        if (c.n_local == 0) continue;
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        EnergyParams P;
+        P.pos = c.pos[h->cur];
+        P.vel = c.vel;
+        P.mass = c.mass;
+        P.kin = c.kin;
+        P.pot = c.pot;
+        P.n = h->n;
+        P.i_global0 = c.i0;
+        P.n_local = c.n_local;
+        const int grid = (int)((c.n_local + kEnergyThreads - 1) / kEnergyThreads);
+        k_energy_terms<<<grid, kEnergyThreads, 0, c.stream>>>(P);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    for (DeviceCtx &c : h->ctx) {
+        if (c.n_local == 0) continue;
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+        buf.resize((size_t)2 * c.n_local);
+        CUDA_TRY(h, cudaMemcpy(buf.data(), c.kin, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost));
+        CUDA_TRY(h, cudaMemcpy(buf.data() + c.n_local, c.pot, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < c.n_local; ++i) {
+            ke += buf[i];
+            pe += buf[c.n_local + i];
+        }
+    }
+    if (!h->single_process && h->nranks > 1) {
+        // combine the per-rank sums (2 doubles) across ranks
+        DeviceCtx &c = h->ctx[0];
+        double two[2] = {(double)ke, (double)pe};
+        CUDA_TRY(h, cudaMemcpy(c.kin, two, sizeof(two), cudaMemcpyHostToDevice));
+        NCCL_TRY(h, ncclAllReduce(c.kin, c.kin, 2, ncclDouble, ncclSum, c.comm, c.stream));
+        CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+        CUDA_TRY(h, cudaMemcpy(two, c.kin, sizeof(two), cudaMemcpyDeviceToHost));
+        ke = two[0];
+        pe = two[1];
+    }
+    if (kinetic) *kinetic = (double)ke;
+    if (potential) *potential = (double)(-0.5L * (long double)kG * pe);   // each pair was counted twice
+    return 0;
+}
+
+int gravity_cuda_timer_start(gravity_cuda_t *h)
+{
+    if (!h) return fail(nullptr, "timer_start: NULL handle");
+    if (join_comm(h) != 0 || sync_all(h) != 0) return -1;
+    h->timing = true;
+    h->hot_launches = 0;
+    h->ctx[0].kev_used = 0;
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaEventRecord(c.ev_start, c.stream));
+    }
+    return 0;
+}
+
+int gravity_cuda_timer_stop(gravity_cuda_t *h, double *ms)
+{
+    if (!h) return fail(nullptr, "timer_stop: NULL handle");
+    if (join_comm(h) != 0) return -1;
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaEventRecord(c.ev_stop, c.stream));
+    }
+    double worst = 0.0;
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaEventSynchronize(c.ev_stop));
+        float t = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&t, c.ev_start, c.ev_stop));
+        worst = std::max(worst, (double)t);
+    }
+    h->timing = false;
+    if (ms) *ms = worst;
+    return 0;
+}
+
+int gravity_cuda_kernel_time(gravity_cuda_t *h, double *ms_total, int64_t *launches)
+{
+    if (!h) return fail(nullptr, "kernel_time: NULL handle");
+    DeviceCtx &c = h->ctx[0];
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+    double total = 0.0;
+    for (size_t k = 0; k + 1 < c.kev_used; k += 2) {
+        float t = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&t, c.kev[k], c.kev[k + 1]));
+        total += t;
+    }
+    if (ms_total) *ms_total = total;
+    if (launches) *launches = (int64_t)(c.kev_used / 2);
+    return 0;
+}
+
+int gravity_cuda_launch_count(const gravity_cuda_t *h, int64_t *launches)
+{
+    if (!h || !launches) return -1;
+    *launches = h->launches;
+    return 0;
+}
+
+int gravity_cuda_fp64_peak(int device, double *tflops, double *sm_mhz)
+{
+    if (check_device(nullptr, device) != 0) return -1;
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(nullptr, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double *sink = nullptr;
+    long long *cycles = nullptr;
+    CUDA_TRY(nullptr, cudaMalloc(&sink, sizeof(double)));
+    CUDA_TRY(nullptr, cudaMalloc(&cycles, sizeof(long long)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(nullptr, cudaEventCreate(&e0));
+    CUDA_TRY(nullptr, cudaEventCreate(&e1));
+    const int grid = sms * 4, threads = 256;
+    int iters = 2000;
+    double best = 0.0, best_mhz = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(nullptr, cudaEventRecord(e0));
+        k_dfma_peak<<<grid, threads>>>(sink, iters, 0.999999, 1e-9, cycles);
+        CUDA_TRY(nullptr, cudaEventRecord(e1));
+        CUDA_TRY(nullptr, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(nullptr, cudaEventElapsedTime(&ms, e0, e1));
+        long long cyc = 0;
+        CUDA_TRY(nullptr, cudaMemcpy(&cyc, cycles, sizeof(cyc), cudaMemcpyDeviceToHost));
+        const double flops = 2.0 * (double)grid * threads * (double)iters * 8.0 * kPeakChains;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep == 0 && ms < 20.f) { iters = (int)(iters * 40.f / std::max(ms, 0.01f)); continue; }
+        if (tf > best) { best = tf; best_mhz = (double)cyc / (ms * 1e-3) / 1e6; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(cycles);
+    if (tflops) *tflops = best;
+    if (sm_mhz) *sm_mhz = best_mhz;
+    return 0;
+}
+
+}  // extern "C"

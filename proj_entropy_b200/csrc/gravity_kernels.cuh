@@ -1,0 +1,590 @@
+// gravity_kernels.cuh -- sm_100a device code of libgravity_cuda.
+//
+// Everything here restates, for the GPU, the arithmetic that is inline in the
+// reference worker thread (sim_gravity.c:1183-1222).  Reference line numbers
+// are cited next to the code that carries the same meaning.
+//
+// Data layout in HBM (per device):
+//   pos[2][npad]   double2 {X,Y}, ping-pong (time t / t+1), ALL bodies replicated
+//   mass[npad]     double, replicated, immutable after upload
+//   vel[chunk]     double2 {VX,VY}, only this device's i-shard
+//   partial[nseg][IB] double2, per work-segment partial sums of the tiled kernel
+// Bodies with global index >= n are padding: mass 0, parked far away, never
+// updated; they contribute exactly 0 to every sum.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gravity {
+
+constexpr int    kTile        = 256;     // j-bodies per shared-memory tile
+constexpr int    kStages      = 4;       // tile ring depth
+constexpr int    kLookahead   = 2;       // tiles in flight ahead of the consumer
+constexpr int    kSmallMax    = 1024;    // largest N of the single-CTA kernel
+constexpr double kG           = 6.673E-11;   // sim_gravity.c:29
+constexpr double kPadCoord    = 1.0e150;     // parking spot of padding bodies
+
+// One contiguous run of j-tiles for one block of i-bodies, executed by one CTA.
+struct Segment {
+    int32_t iblock;       // which block of IB = THREADS*R local i-bodies
+    int32_t tile_begin;   // first j-tile (units of kTile bodies)
+    int32_t tile_end;     // one past the last j-tile
+    int32_t slot;         // which partial[] row this segment writes
+};
+
+struct AccumParams {
+    const double2 *pos;             // time-t positions of all bodies
+    const double  *mass;
+    const double2 *vel;             // local shard
+    double2       *partial;         // [nseg][IB]
+    const Segment *seg;
+    const int32_t *cta_seg_begin;   // [gridDim.x + 1]
+    int64_t        i_global0;       // global index of local body 0
+    int64_t        n_local;         // real bodies in the local shard
+    double         dt;              // (double)DT
+};
+
+struct CommitParams {
+    const double2 *pos_cur;         // time-t positions (all bodies)
+    double2       *pos_next;        // time-t+1 positions (all bodies; we write our shard)
+    double2       *vel;             // local shard, updated in place
+    const double  *mass;
+    const double2 *partial;
+    const int32_t *iblock_seg_begin;    // [n_iblock + 1]
+    double2       *accel_out;       // local shard, used when export_accel
+    int64_t        n;               // real bodies, all shards
+    int64_t        i_global0;
+    int64_t        n_local;
+    int32_t        iblock_size;     // IB of the accumulate kernel
+    int32_t        export_accel;    // 1: write AX,AY and leave the state alone
+    double         dt;
+};
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP)
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Arithmetic
+// ---------------------------------------------------------------------------
+
+// MUFU.RSQ64H: ~20-bit reciprocal square root from the high word of r2.
+__device__ __forceinline__ double rsqrt_seed(double r2)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+    return y;
+}
+
+// The evaluated body's temporary position, sim_gravity.c:1186-1187:
+// X + VX*DT/2 evaluated as X + ((VX*DT)/2), no contraction.
+__device__ __forceinline__ double half_drift(double x, double v, double dt)
+{
+    return __dadd_rn(x, __dmul_rn(__dmul_rn(v, dt), 0.5));
+}
+
+// One pair, sim_gravity.c:1193-1204, as 13 FP64-pipe instructions.
+//   w = m * r2^(-3/2) from the seed y0:  with e = 1 - r2*y0^2 (one exact FMA,
+//   y0^2 is exact because y0 has 20 significant bits),
+//   r2^(-3/2) = y0^3 * (1-e)^(-3/2) = y0^3 * (1 + e*(3/2 + 15/8 e) + O(e^3)),
+//   |e| < 2^-19 so the dropped term is < 2^-56.
+// r2 == 0 (an exactly coincident pair, :1199-1201) or a non-finite r2 yields a
+// NaN that poisons the sum; the commit kernel detects it and redoes that body
+// on the guarded path, which keeps the test out of this loop.
+__device__ __forceinline__ double pair_weight(double dx, double dy, double mj)
+{
+    const double r2 = fma(dy, dy, dx * dx);
+    const double y0 = rsqrt_seed(r2);
+    const double b  = y0 * y0;
+    const double e  = fma(-r2, b, 1.0);
+    const double a  = mj * y0;
+    const double w0 = a * b;
+    const double p  = fma(1.875, e, 1.5);
+    const double g  = fma(e, p, 1.0);
+    return w0 * g;
+}
+
+// The same pair exactly as the reference evaluates it (sim_gravity.c:1196-1204):
+// correctly rounded IEEE sqrt and divide, no FMA contraction.
+__device__ __forceinline__ void pair_strict(double xj, double yj, double mj, double px, double py,
+                                            double &sx, double &sy)
+{
+    const double dx = __dsub_rn(xj, px);
+    const double dy = __dsub_rn(yj, py);
+    const double r  = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    if (r == 0.0) return;                                        // :1199-1201
+    const double t  = __ddiv_rn(mj, __dmul_rn(__dmul_rn(r, r), r));  // :1202
+    sx = __dadd_rn(sx, __dmul_rn(t, dx));                        // :1203
+    sy = __dadd_rn(sy, __dmul_rn(t, dy));                        // :1204
+}
+
+// sim_gravity.c:1207-1221 with the reference's association and no contraction:
+//   A = G*SUM; D = V1*DT + ((0.5*A)*DT)*DT; V2 = V1 + A*DT; NEXT = P + D.
+__device__ __forceinline__ void kick_drift(double sum, double dt, double p, double v,
+                                           double &p_next, double &v_next, double &a)
+{
+    a = __dmul_rn(kG, sum);
+    const double d = __dadd_rn(__dmul_rn(v, dt), __dmul_rn(__dmul_rn(__dmul_rn(0.5, a), dt), dt));
+    v_next = __dadd_rn(v, __dmul_rn(a, dt));
+    p_next = __dadd_rn(p, d);
+}
+
+// ---------------------------------------------------------------------------
+// K1: tiled pair accumulation (the hot kernel)
+// ---------------------------------------------------------------------------
+//
+// Work = n_iblock x n_tile units (IB i-bodies against one j-tile).  The host
+// flattens the units i-block-major and gives each CTA an equal contiguous run
+// (a few Segments), so that one wave of SMs x ctas_per_sm CTAs finishes
+// together whatever N is.  Each thread keeps R i-bodies (half-drifted position
+// + 2 accumulators) in registers; j-tiles arrive in a 4-deep shared-memory
+// ring filled by 1-D bulk copies issued by thread 0 and signalled through
+// mbarriers; every lane reads the same j, so the LDS are broadcasts.
+
+template <int THREADS, int R, bool DIAG>
+__device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, const double *__restrict__ sm,
+                                             const double (&xi)[R], const double (&yi)[R],
+                                             double (&ax)[R], double (&ay)[R],
+                                             const int64_t (&gi)[R], int64_t gj0)
+{
+#pragma unroll 4
+    for (int j = 0; j < kTile; ++j) {
+        const double2 pj = sp[j];
+        const double  mj = sm[j];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double dx = pj.x - xi[r];
+            const double dy = pj.y - yi[r];
+            double w = pair_weight(dx, dy, mj);
+            if (DIAG) {
+                // self is skipped by index (sim_gravity.c:1191): its distance
+                // is |V*DT/2|, not 0, because only the i-body is drifted.
+                w = (gj0 + j == gi[r]) ? 0.0 : w;
+            }
+            ax[r] = fma(w, dx, ax[r]);
+            ay[r] = fma(w, dy, ay[r]);
+        }
+    }
+}
+
+template <int THREADS, int R, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumParams P)
+{
+    constexpr int      IB         = THREADS * R;
+    constexpr int      kWarps     = THREADS / 32;
+    constexpr uint32_t kTileBytes = kTile * (sizeof(double2) + sizeof(double));
+
+    __shared__ alignas(128) double2 s_pos[kStages][kTile];
+    __shared__ alignas(128) double  s_mass[kStages][kTile];
+    __shared__ alignas(8) uint64_t  s_full[kStages];
+    __shared__ alignas(8) uint64_t  s_empty[kStages];
+
+    const int tid  = threadIdx.x;
+    const int lane = tid & 31;
+
+    const int seg_begin = P.cta_seg_begin[blockIdx.x];
+    const int seg_end   = P.cta_seg_begin[blockIdx.x + 1];
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer cursor (meaningful in thread 0 only)
+    int p_seg = seg_begin, p_tile = 0, p_tile_end = 0, issued = 0;
+    if (tid == 0 && p_seg < seg_end) {
+        p_tile     = P.seg[p_seg].tile_begin;
+        p_tile_end = P.seg[p_seg].tile_end;
+    }
+    auto issue_next = [&]() {
+        if (p_seg >= seg_end) return;
+        const int stage = issued % kStages;
+        if (issued >= kStages) mbar_wait(&s_empty[stage], ((issued / kStages) - 1) & 1);
+        mbar_arrive_expect_tx(&s_full[stage], kTileBytes);
+        bulk_load(&s_pos[stage][0], P.pos + (size_t)p_tile * kTile, kTile * sizeof(double2), &s_full[stage]);
+        bulk_load(&s_mass[stage][0], P.mass + (size_t)p_tile * kTile, kTile * sizeof(double), &s_full[stage]);
+        ++issued;
+        if (++p_tile == p_tile_end) {
+            if (++p_seg < seg_end) {
+                p_tile     = P.seg[p_seg].tile_begin;
+                p_tile_end = P.seg[p_seg].tile_end;
+            }
+        }
+    };
+    if (tid == 0) {
+        for (int k = 0; k < kLookahead; ++k) issue_next();
+    }
+
+    int consumed = 0;
+    for (int s = seg_begin; s < seg_end; ++s) {
+        const Segment sg = P.seg[s];
+        const int64_t li0 = (int64_t)sg.iblock * IB;     // first local i of the block
+
+        double  xi[R], yi[R], ax[R], ay[R];
+        int64_t gi[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t li = li0 + (int64_t)r * THREADS + tid;
+            gi[r] = P.i_global0 + li;
+            ax[r] = 0.0;
+            ay[r] = 0.0;
+            if (li < P.n_local) {
+                const double2 p = P.pos[gi[r]];
+                const double2 v = P.vel[li];
+                xi[r] = half_drift(p.x, v.x, P.dt);      // sim_gravity.c:1186
+                yi[r] = half_drift(p.y, v.y, P.dt);      // sim_gravity.c:1187
+            } else {
+                xi[r] = 0.0;
+                yi[r] = 0.0;
+                gi[r] = -1;
+            }
+        }
+        const int64_t gi_lo = P.i_global0 + li0;
+        const int64_t gi_hi = gi_lo + IB;
+
+        for (int t = sg.tile_begin; t < sg.tile_end; ++t) {
+            if (tid == 0) issue_next();
+            const int stage = consumed % kStages;
+            mbar_wait(&s_full[stage], (consumed / kStages) & 1);
+
+            const int64_t gj0 = (int64_t)t * kTile;
+            if (gj0 < gi_hi && gj0 + kTile > gi_lo) {
+                consume_tile<THREADS, R, true>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
+            } else {
+                consume_tile<THREADS, R, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            ++consumed;
+        }
+
+        double2 *out = P.partial + (size_t)sg.slot * IB;
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r * THREADS + tid] = make_double2(ax[r], ay[r]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Commit: reduce the partials, repair poisoned bodies, kick + drift
+// ---------------------------------------------------------------------------
+
+// Guarded evaluation of one body by a whole CTA: the reference's own formula
+// per pair (sqrt, divide, both skips), lanes striding over j, fixed-shape tree
+// reduction (deterministic).  Only bodies whose fast sum came out non-finite
+// get here -- in practice bodies that coincide exactly with another body.
+__device__ inline void block_guarded_body(const CommitParams &P, int64_t gi, double px, double py,
+                                          double *s_red, double &sx, double &sy)
+{
+    double tx = 0.0, ty = 0.0;
+    for (int64_t j = threadIdx.x; j < P.n; j += blockDim.x) {
+        if (j == gi) continue;                            // sim_gravity.c:1191
+        const double2 pj = P.pos_cur[j];
+        pair_strict(pj.x, pj.y, P.mass[j], px, py, tx, ty);
+    }
+    s_red[threadIdx.x]              = tx;
+    s_red[blockDim.x + threadIdx.x] = ty;
+    __syncthreads();
+    for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            s_red[threadIdx.x]              += s_red[threadIdx.x + w];
+            s_red[blockDim.x + threadIdx.x] += s_red[blockDim.x + threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    sx = s_red[0];
+    sy = s_red[blockDim.x];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void commit_body(const CommitParams &P, int64_t li, double sx, double sy)
+{
+    const int64_t gi = P.i_global0 + li;
+    const double2 p  = P.pos_cur[gi];
+    const double2 v  = P.vel[li];
+    double nx, ny, nvx, nvy, ax, ay;
+    kick_drift(sx, P.dt, p.x, v.x, nx, nvx, ax);
+    kick_drift(sy, P.dt, p.y, v.y, ny, nvy, ay);
+    if (P.export_accel) {
+        P.accel_out[li] = make_double2(ax, ay);          // sim_gravity.c:1207-1208
+    } else {
+        P.pos_next[gi] = make_double2(nx, ny);           // NEXT_X, NEXT_Y  (:1218-1219)
+        P.vel[li]      = make_double2(nvx, nvy);         // NEXT_VX, NEXT_VY (:1220-1221)
+    }
+}
+
+constexpr int kCommitThreads = 256;
+
+__global__ void __launch_bounds__(kCommitThreads) k_commit_partials(const CommitParams P)
+{
+    __shared__ double  s_red[2 * kCommitThreads];
+    __shared__ int     s_bad[kCommitThreads];
+    __shared__ int     s_nbad;
+    __shared__ double2 s_fixed[kCommitThreads];
+
+    const int64_t li     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool    active = li < P.n_local;
+    double sx = 0.0, sy = 0.0;
+    if (active) {
+        const int64_t ib  = li / P.iblock_size;
+        const int64_t off = li - ib * P.iblock_size;
+        const int     s0  = P.iblock_seg_begin[ib];
+        const int     s1  = P.iblock_seg_begin[ib + 1];
+        for (int s = s0; s < s1; ++s) {                  // fixed order: deterministic
+            const double2 part = P.partial[(size_t)s * P.iblock_size + off];
+            sx += part.x;
+            sy += part.y;
+        }
+    }
+    if (threadIdx.x == 0) s_nbad = 0;
+    __syncthreads();
+    const bool bad = active && !(isfinite(sx) && isfinite(sy));
+    if (bad) s_bad[atomicAdd(&s_nbad, 1)] = threadIdx.x;
+    __syncthreads();
+    const int nbad = s_nbad;
+    for (int b = 0; b < nbad; ++b) {
+        const int     owner = s_bad[b];
+        const int64_t oli   = (int64_t)blockIdx.x * blockDim.x + owner;
+        const int64_t ogi   = P.i_global0 + oli;
+        const double2 p     = P.pos_cur[ogi];
+        const double2 v     = P.vel[oli];
+        double fx, fy;
+        block_guarded_body(P, ogi, half_drift(p.x, v.x, P.dt), half_drift(p.y, v.y, P.dt), s_red, fx, fy);
+        if (threadIdx.x == 0) s_fixed[owner] = make_double2(fx, fy);
+    }
+    __syncthreads();
+    if (bad) {
+        sx = s_fixed[threadIdx.x].x;
+        sy = s_fixed[threadIdx.x].y;
+    }
+    if (active) commit_body(P, li, sx, sy);
+}
+
+// ---------------------------------------------------------------------------
+// STRICT kernels: bit-identical to the reference loop
+// ---------------------------------------------------------------------------
+
+// Any N: one thread per local i-body, j ascending through shared-memory tiles.
+constexpr int kStrictThreads = 128;
+
+__global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitParams P)
+{
+    __shared__ double2 s_pos[kStrictThreads];
+    __shared__ double  s_mass[kStrictThreads];
+
+    const int64_t li     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool    active = li < P.n_local;
+    const int64_t gi     = P.i_global0 + li;
+    double px = 0.0, py = 0.0, sx = 0.0, sy = 0.0;
+    if (active) {
+        const double2 p = P.pos_cur[gi];
+        const double2 v = P.vel[li];
+        px = half_drift(p.x, v.x, P.dt);
+        py = half_drift(p.y, v.y, P.dt);
+    }
+    for (int64_t j0 = 0; j0 < P.n; j0 += kStrictThreads) {
+        const int64_t j = j0 + threadIdx.x;
+        __syncthreads();
+        if (j < P.n) {
+            s_pos[threadIdx.x]  = P.pos_cur[j];
+            s_mass[threadIdx.x] = P.mass[j];
+        }
+        __syncthreads();
+        const int cnt = (int)min((int64_t)kStrictThreads, P.n - j0);
+        if (active) {
+            for (int jj = 0; jj < cnt; ++jj) {
+                if (j0 + jj == gi) continue;             // sim_gravity.c:1191
+                pair_strict(s_pos[jj].x, s_pos[jj].y, s_mass[jj], px, py, sx, sy);
+            }
+        }
+    }
+    if (active) commit_body(P, li, sx, sy);
+}
+
+// N <= 1024, one device: the whole system lives in one CTA and `nsteps` steps
+// run inside one launch (two __syncthreads per step replace the reference's
+// two spin barriers, sim_gravity.c:1140 and :1226).
+__global__ void __launch_bounds__(kSmallMax) k_small_strict_steps(double2 *pos, double2 *vel,
+                                                                  const double *mass, int n, double dt,
+                                                                  long long nsteps)
+{
+    __shared__ double2 s_pos[kSmallMax];
+    __shared__ double  s_mass[kSmallMax];
+
+    const int  i      = threadIdx.x;
+    const bool active = i < n;
+    double2 p = make_double2(0.0, 0.0), v = make_double2(0.0, 0.0);
+    if (active) {
+        p         = pos[i];
+        v         = vel[i];
+        s_mass[i] = mass[i];
+    }
+    for (long long s = 0; s < nsteps; ++s) {
+        if (active) s_pos[i] = p;
+        __syncthreads();
+        if (active) {
+            const double px = half_drift(p.x, v.x, dt);
+            const double py = half_drift(p.y, v.y, dt);
+            double sx = 0.0, sy = 0.0;
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                pair_strict(s_pos[j].x, s_pos[j].y, s_mass[j], px, py, sx, sy);
+            }
+            double ax, ay;
+            kick_drift(sx, dt, p.x, v.x, p.x, v.x, ax);
+            kick_drift(sy, dt, p.y, v.y, p.y, v.y, ay);
+        }
+        __syncthreads();
+    }
+    if (active) {
+        pos[i] = p;
+        vel[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4: energy diagnostic (per-body terms; the host adds them up)
+// ---------------------------------------------------------------------------
+
+struct EnergyParams {
+    const double2 *pos;
+    const double2 *vel;     // local shard
+    const double  *mass;
+    double        *kin;     // local shard: 1/2 m |v|^2
+    double        *pot;     // local shard: m_i * sum_{j != i} m_j / r_ij
+    int64_t        n, i_global0, n_local;
+};
+
+constexpr int kEnergyThreads = 128;
+
+__global__ void __launch_bounds__(kEnergyThreads) k_energy_terms(const EnergyParams P)
+{
+    __shared__ double2 s_pos[kEnergyThreads];
+    __shared__ double  s_mass[kEnergyThreads];
+
+    const int64_t li     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool    active = li < P.n_local;
+    const int64_t gi     = P.i_global0 + li;
+    double2 p = make_double2(0.0, 0.0);
+    if (active) p = P.pos[gi];
+    double acc = 0.0;
+    for (int64_t j0 = 0; j0 < P.n; j0 += kEnergyThreads) {
+        const int64_t j = j0 + threadIdx.x;
+        __syncthreads();
+        if (j < P.n) {
+            s_pos[threadIdx.x]  = P.pos[j];
+            s_mass[threadIdx.x] = P.mass[j];
+        }
+        __syncthreads();
+        const int cnt = (int)min((int64_t)kEnergyThreads, P.n - j0);
+#pragma unroll 4
+        for (int jj = 0; jj < cnt; ++jj) {
+            const double dx = s_pos[jj].x - p.x;
+            const double dy = s_pos[jj].y - p.y;
+            const double r2 = fma(dy, dy, dx * dx);
+            if (r2 > 0.0 && j0 + jj != gi) {
+                const double y0 = rsqrt_seed(r2);
+                const double e  = fma(-r2, y0 * y0, 1.0);
+                const double y  = fma(y0 * e, fma(0.375, e, 0.5), y0);   // 1/r
+                acc = fma(s_mass[jj], y, acc);
+            }
+        }
+    }
+    if (active) {
+        const double2 v = P.vel[li];
+        const double  m = P.mass[gi];
+        P.kin[li] = 0.5 * m * (v.x * v.x + v.y * v.y);
+        P.pot[li] = m * acc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 FMA-pipe microbenchmark (roofline denominator measured on the box)
+// ---------------------------------------------------------------------------
+
+constexpr int kPeakChains = 8;
+
+__global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, double a, double b,
+                                                   long long *cycles)
+{
+    double acc[kPeakChains];
+#pragma unroll
+    for (int c = 0; c < kPeakChains; ++c) acc[c] = (double)(threadIdx.x + c);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int c = 0; c < kPeakChains; ++c) acc[c] = fma(acc[c], a, b);
+        }
+    }
+    const long long t1 = clock64();
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < kPeakChains; ++c) s += acc[c];
+    if (s == 123.456) sink[0] = s;                      // keeps the chains alive
+    if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+// Parks padding bodies (global index >= n): mass 0, far away, never updated.
+__global__ void k_init_padding(double2 *pos0, double2 *pos1, double *mass, int64_t n, int64_t npad)
+{
+    const int64_t i = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npad) {
+        pos0[i] = make_double2(kPadCoord, kPadCoord);
+        pos1[i] = make_double2(kPadCoord, kPadCoord);
+        mass[i] = 0.0;
+    }
+}
+
+}  // namespace gravity

@@ -1,0 +1,214 @@
+"""ctypes mirror of include/gravity_cuda.h (the C ABI of libgravity_cuda).
+
+Names, argument meaning and error behaviour follow the header one to one; a
+negative return code becomes GravityError carrying gravity_cuda_last_error().
+There is no fallback of any kind: if the shared library is missing this module
+raises at first use, and on a box without an sm_100 GPU `GravityCuda(...)`
+raises with the library's own message.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+KERNEL_AUTO, KERNEL_TILED, KERNEL_STRICT = 0, 1, 2
+NCCL_ID_BYTES = 128
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_dp = C.POINTER(C.c_double)
+
+
+class GravityError(RuntimeError):
+    pass
+
+
+def load_cuda_library():
+    """Load proj_entropy_b200/libgravity_cuda.so and declare every prototype."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "libgravity_cuda.so")
+    if not os.path.exists(path):
+        raise GravityError("%s is not built (run `make` or __graft_entry__.build()); "
+                           "there is no fallback implementation" % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    H = C.c_void_p
+    sigs = {
+        "gravity_cuda_device_count": (C.c_int, []),
+        "gravity_cuda_last_error": (C.c_char_p, [H]),
+        "gravity_cuda_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+        "gravity_cuda_create": (C.c_int, [C.POINTER(H), C.c_int64, C.c_int]),
+        "gravity_cuda_create_rank": (C.c_int, [C.POINTER(H), C.c_int64, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_size_t]),
+        "gravity_cuda_destroy": (None, [H]),
+        "gravity_cuda_set_option": (C.c_int, [H, C.c_char_p, C.c_int64]),
+        "gravity_cuda_upload": (C.c_int, [H, _dp, _dp, _dp, _dp, _dp]),
+        "gravity_cuda_download": (C.c_int, [H, _dp, _dp, _dp, _dp]),
+        "gravity_cuda_step": (C.c_int, [H, C.c_int32, C.c_int64]),
+        "gravity_cuda_step_async": (C.c_int, [H, C.c_int32, C.c_int64]),
+        "gravity_cuda_sync": (C.c_int, [H]),
+        "gravity_cuda_accel": (C.c_int, [H, C.c_int32, _dp, _dp]),
+        "gravity_cuda_step_objects": (C.c_int, [H, C.POINTER(C.c_void_p), C.c_int64, C.c_size_t, C.c_size_t,
+                                                C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_int64]),
+        "gravity_cuda_energy": (C.c_int, [H, _dp, _dp]),
+        "gravity_cuda_timer_start": (C.c_int, [H]),
+        "gravity_cuda_timer_stop": (C.c_int, [H, _dp]),
+        "gravity_cuda_launch_count": (C.c_int, [H, C.POINTER(C.c_int64)]),
+        "gravity_cuda_kernel_time": (C.c_int, [H, _dp, C.POINTER(C.c_int64)]),
+        "gravity_cuda_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._declared = sorted(sigs)
+    _LIB = lib
+    return lib
+
+
+def _f64(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.shape != (n,):
+        raise ValueError("expected %d doubles, got shape %s" % (n, a.shape))
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def device_count():
+    return load_cuda_library().gravity_cuda_device_count()
+
+
+def nccl_unique_id():
+    lib = load_cuda_library()
+    buf = (C.c_ubyte * NCCL_ID_BYTES)()
+    if lib.gravity_cuda_nccl_unique_id(buf, NCCL_ID_BYTES) != 0:
+        raise GravityError(lib.gravity_cuda_last_error(None).decode())
+    return bytes(buf)
+
+
+def fp64_peak(device=0):
+    """(TFLOP/s of the FP64 FMA pipe measured by a DFMA microbenchmark, SM MHz)."""
+    lib = load_cuda_library()
+    tf, mhz = C.c_double(), C.c_double()
+    if lib.gravity_cuda_fp64_peak(device, C.byref(tf), C.byref(mhz)) != 0:
+        raise GravityError(lib.gravity_cuda_last_error(None).decode())
+    return tf.value, mhz.value
+
+
+class GravityCuda:
+    """One gravity_cuda_t handle.
+
+    GravityCuda(n, ngpus=k)                         -> gravity_cuda_create
+    GravityCuda(n, rank=r, nranks=p, device=d, nccl_id=b) -> gravity_cuda_create_rank
+    """
+
+    def __init__(self, n, ngpus=1, rank=None, nranks=None, device=0, nccl_id=None, **options):
+        self._lib = load_cuda_library()
+        self._h = C.c_void_p()
+        self.n = int(n)
+        if rank is None:
+            rc = self._lib.gravity_cuda_create(C.byref(self._h), self.n, int(ngpus))
+        else:
+            idbuf = None
+            if nccl_id is not None:
+                idbuf = (C.c_ubyte * NCCL_ID_BYTES).from_buffer_copy(nccl_id)
+            rc = self._lib.gravity_cuda_create_rank(C.byref(self._h), self.n, int(rank), int(nranks), int(device),
+                                                    idbuf, NCCL_ID_BYTES if idbuf is not None else 0)
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise GravityError(self._lib.gravity_cuda_last_error(None).decode())
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    # -- plumbing -----------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise GravityError(self._lib.gravity_cuda_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._lib.gravity_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the C ABI, one method per entry point --------------------------------
+    def set_option(self, key, value):
+        self._check(self._lib.gravity_cuda_set_option(self._h, key.encode(), int(value)))
+
+    def upload(self, mass, x, y, vx, vy):
+        n = self.n
+        arrs = [_f64(a, n) for a in (mass, x, y, vx, vy)]
+        self._check(self._lib.gravity_cuda_upload(self._h, *[_ptr(a) for a in arrs]))
+
+    def upload_ptrs(self, mass, x, y, vx, vy):
+        """Raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        cast = lambda p: C.cast(C.c_void_p(int(p)), _dp)
+        self._check(self._lib.gravity_cuda_upload(self._h, cast(mass), cast(x), cast(y), cast(vx), cast(vy)))
+
+    def download_ptrs(self, x, y, vx, vy):
+        cast = lambda p: C.cast(C.c_void_p(int(p)), _dp) if p else None
+        self._check(self._lib.gravity_cuda_download(self._h, cast(x), cast(y), cast(vx), cast(vy)))
+
+    def download(self):
+        out = [np.empty(self.n, dtype=np.float64) for _ in range(4)]
+        self._check(self._lib.gravity_cuda_download(self._h, *[_ptr(a) for a in out]))
+        return tuple(out)
+
+    def step(self, dt, nsteps=1):
+        self._check(self._lib.gravity_cuda_step(self._h, int(dt), int(nsteps)))
+
+    def step_async(self, dt, nsteps=1):
+        self._check(self._lib.gravity_cuda_step_async(self._h, int(dt), int(nsteps)))
+
+    def sync(self):
+        self._check(self._lib.gravity_cuda_sync(self._h))
+
+    def accel(self, dt):
+        ax = np.empty(self.n, dtype=np.float64)
+        ay = np.empty(self.n, dtype=np.float64)
+        self._check(self._lib.gravity_cuda_accel(self._h, int(dt), _ptr(ax), _ptr(ay)))
+        return ax, ay
+
+    def step_objects(self, object_ptrs, off_x, off_y, off_vx, off_vy, off_mass, dt, nsteps=1):
+        n = len(object_ptrs)
+        arr = (C.c_void_p * n)(*object_ptrs)
+        self._check(self._lib.gravity_cuda_step_objects(self._h, arr, n, off_x, off_y, off_vx, off_vy, off_mass,
+                                                        int(dt), int(nsteps)))
+
+    def energy(self):
+        ke, pe = C.c_double(), C.c_double()
+        self._check(self._lib.gravity_cuda_energy(self._h, C.byref(ke), C.byref(pe)))
+        return ke.value, pe.value
+
+    def timer_start(self):
+        self._check(self._lib.gravity_cuda_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self._lib.gravity_cuda_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        v = C.c_int64()
+        self._check(self._lib.gravity_cuda_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def kernel_time(self):
+        ms, cnt = C.c_double(), C.c_int64()
+        self._check(self._lib.gravity_cuda_kernel_time(self._h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value

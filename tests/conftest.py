@@ -1,0 +1,66 @@
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE_DIR = "/root/reference"          # exists only in the build container
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "multigpu: needs at least 2 GPUs")
+
+
+def hexarr(values):
+    """List of C99 hex-float strings -> float64 array, bit exact."""
+    return np.array([float.fromhex(v) for v in values], dtype=np.float64)
+
+
+def load_fixture(name):
+    fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    if "error" not in fx:
+        fx["mass_f"] = hexarr(fx["mass"])
+        for cp in fx["checkpoints"]:
+            for k in ("x", "y", "vx", "vy"):
+                cp[k + "_f"] = hexarr(cp[k])
+    return fx
+
+
+def fixture_names(prefix=""):
+    return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(GOLDEN, prefix + "*.json")))
+
+
+def ok_fixture_names(prefix=""):
+    return [n for n in fixture_names(prefix) if "error" not in json.load(open(os.path.join(GOLDEN, n + ".json")))]
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(np.all(a.view(np.uint64) == b.view(np.uint64)))
+
+
+def scenario_path(fx):
+    """Where the text file of a fixture lives on this box, or None."""
+    kind, rel = fx["source"].split(":", 1)
+    p = os.path.join(REFERENCE_DIR, rel) if kind == "reference" else os.path.join(ROOT, rel)
+    return p if os.path.exists(p) else None
+
+
+def rel_err_rows(ax, ay, rx, ry):
+    """Per-body relative error of a 2-vector: |a - r|_2 / |r|_2."""
+    num = np.hypot(ax - rx, ay - ry)
+    den = np.hypot(rx, ry)
+    return num / np.where(den > 0, den, 1.0)
+
+
+@pytest.fixture(scope="session")
+def gpu_count():
+    import proj_entropy_b200 as g
+    return g.device_count()

@@ -1,0 +1,98 @@
+"""The product's scenario reader (libgravity_host, gravity_scenario_load) against
+what the reference's own parser (sim_gravity_init, sim_gravity.c:197-422)
+produced for the same file, recorded in tests/golden/ by the unmodified TU."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import proj_entropy_b200 as g
+from conftest import GOLDEN, bits_equal, fixture_names, load_fixture, scenario_path
+
+
+def _cases():
+    out = []
+    for name in fixture_names():
+        fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
+        out.append(pytest.param(name, id=name))
+    return out
+
+
+@pytest.mark.parametrize("name", _cases())
+def test_reader_matches_reference_parser(name):
+    fx = load_fixture(name)
+    path = scenario_path(fx)
+    if path is None:
+        pytest.skip("scenario text lives in /root/reference (build container only)")
+    assert hashlib.md5(open(path, "rb").read()).hexdigest() == fx["file_md5"]
+    if "error" in fx:
+        with pytest.raises(g.ScenarioError) as ei:
+            g.load_scenario(path)
+        rows = ei.value.rows
+        assert rows[0] == fx["error"][0]
+        assert os.path.basename(rows[1]) == fx["error"][1]
+        assert rows[2] == fx["error"][2]
+        return
+    s = g.load_scenario(path)
+    cp0 = fx["checkpoints"][0]
+    assert s.n == fx["n"]
+    assert s.dt == fx["dt"]
+    assert s.sim_width == float.fromhex(fx["sim_width"])
+    assert s.names == fx["names"]
+    assert s.sim_name == os.path.basename(path).upper()[:31]
+    assert bits_equal(s.mass, fx["mass_f"])
+    assert bits_equal(s.radius, [float.fromhex(v) for v in fx["radius"]])
+    for got, key in ((s.x, "x_f"), (s.y, "y_f"), (s.vx, "vx_f"), (s.vy, "vy_f")):
+        assert bits_equal(got, cp0[key]), key
+
+
+def test_open_failed_rows():
+    with pytest.raises(g.ScenarioError) as ei:
+        g.load_scenario("/nonexistent/scenario")
+    assert ei.value.rows[0] == "Open Failed" and ei.value.rows[1] == "/nonexistent/scenario"
+
+
+def test_empty_file_fails_to_open(tmp_path):
+    p = tmp_path / "empty"
+    p.write_text("")
+    with pytest.raises(g.ScenarioError) as ei:
+        g.load_scenario(str(p))
+    assert ei.value.rows[0] == "Open Failed"      # util.c:1761-1765: a zero-length read is an error
+
+
+def test_params_are_inherited_when_absent():
+    fx = load_fixture("own_no_params")
+    path = scenario_path(fx)
+    assert g.load_scenario(path).dt == 0 == fx["dt"]          # fresh process: statics are zero
+    s = g.load_scenario(path, inherit_dt=30, inherit_sim_width=5.0)
+    assert s.dt == 30 and s.sim_width == 5.0                  # sim_gravity.c:222-223
+
+
+def test_object_cap(tmp_path):
+    p = tmp_path / "many"
+    p.write_text("PARAM DT_LINUX 1 SEC\n" + "".join("b%d %d 0 0 0 1E20 1 RED 1\n" % (i, i * 1000) for i in range(250)))
+    assert g.load_scenario(str(p)).n == 200                   # MAX_OBJECT, sim_gravity.c:398-401
+    assert g.load_scenario(str(p), max_objects=1000).n == 250  # extension for large hosts
+
+
+def test_tab_only_line_is_not_blank(tmp_path):
+    # only ' ' counts as blank (sim_gravity.c:280-285); a tab goes on to the
+    # object scan and fails it
+    p = tmp_path / "tab"
+    p.write_text("a 0 0 0 0 1E30 1 RED 1\n\t\n")
+    with pytest.raises(g.ScenarioError) as ei:
+        g.load_scenario(str(p))
+    assert ei.value.rows[0] == "Invalid Object" and ei.value.rows[2] == "line 2"
+
+
+def test_save_round_trip(tmp_path):
+    fx = load_fixture("own_nested_indent")
+    s = g.load_scenario(scenario_path(fx))
+    out = tmp_path / "saved"
+    s.save(str(out))
+    t = g.load_scenario(str(out))
+    assert t.n == s.n and t.dt == s.dt and t.sim_width == s.sim_width and t.names == s.names
+    for k in ("mass", "radius", "x", "y", "vx", "vy"):
+        assert bits_equal(getattr(s, k), getattr(t, k)), k      # %.17g round-trips doubles
