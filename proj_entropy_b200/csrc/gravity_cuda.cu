@@ -70,7 +70,7 @@ struct gravity_cuda {
     int cur = 0;                     // which pos[] holds time t
     bool uploaded = false, planned = false;
     int opt_kernel = GRAVITY_CUDA_KERNEL_AUTO;
-    int opt_threads = 256, opt_bpt = 2, opt_ctas_per_sm = 2, opt_overlap = 0;
+    int opt_threads = 256, opt_bpt = 4, opt_ctas_per_sm = 1, opt_overlap = 0;
     int64_t launches = 0;
     bool timing = false;
     int64_t hot_launches = 0;
@@ -931,8 +931,9 @@ int gravity_cuda_fp64_peak(int device, double *tflops, double *sm_mhz)
     int iters = 2000;
     double best = 0.0, best_mhz = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(nullptr, cudaMemset(cycles, 0, sizeof(long long)));
         CUDA_TRY(nullptr, cudaEventRecord(e0));
-        k_dfma_peak<<<grid, threads>>>(sink, iters, 0.999999, 1e-9, cycles);
+        k_dfma_peak<<<grid, threads>>>(sink, iters, 0.25, 1e-12, cycles);
         CUDA_TRY(nullptr, cudaEventRecord(e1));
         CUDA_TRY(nullptr, cudaEventSynchronize(e1));
         float ms = 0.f;

@@ -554,18 +554,25 @@ __global__ void __launch_bounds__(kEnergyThreads) k_energy_terms(const EnergyPar
 
 constexpr int kPeakChains = 8;
 
+// Each FMA reads two distinct register pairs plus an immediate.  That is the
+// form that reaches the pipe's 1 warp-instruction / 2 cycles / sub-partition;
+// an FMA with three distinct register operands is limited by register-file
+// read bandwidth to ~1 per 3 cycles (tools/fp64_microbench.cu).
 __global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, double a, double b,
                                                    long long *cycles)
 {
-    double acc[kPeakChains];
+    double acc[kPeakChains], x[kPeakChains];
 #pragma unroll
-    for (int c = 0; c < kPeakChains; ++c) acc[c] = (double)(threadIdx.x + c);
+    for (int c = 0; c < kPeakChains; ++c) {
+        acc[c] = (double)(threadIdx.x + c);
+        x[c]   = a + (double)(threadIdx.x * kPeakChains + c) * b;
+    }
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
 #pragma unroll
-            for (int c = 0; c < kPeakChains; ++c) acc[c] = fma(acc[c], a, b);
+            for (int c = 0; c < kPeakChains; ++c) acc[c] = fma(acc[c], x[c], 1.5);
         }
     }
     const long long t1 = clock64();
@@ -573,7 +580,9 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, doub
 #pragma unroll
     for (int c = 0; c < kPeakChains; ++c) s += acc[c];
     if (s == 123.456) sink[0] = s;                      // keeps the chains alive
-    if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
+    // the warp arbiter lets some CTAs of an SM finish long before others; the
+    // longest-lived thread spans the whole kernel
+    if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long *)cycles, (unsigned long long)(t1 - t0));
 }
 
 // Parks padding bodies (global index >= n): mass 0, far away, never updated.

@@ -1,0 +1,210 @@
+/*
+ * gravity_headless.c -- headless C host for libgravity_cuda.
+ *
+ * This is the reference's worker loop (sim_gravity_thread,
+ * sim_gravity.c:1130-1273) with the display split off: the body of
+ * `if (local_state == STATE_RUN)` is one gravity_cuda_step() call, and what
+ * the reference keeps around it stays here in host C -- the simulation clock
+ * (sim_time += DT, :1255), the once-per-day PATH ring sampling (:1232-1236,
+ * :1248-1251, :1258-1260) and the RATE Y/S readout (:912-919).  Steps are
+ * batched up to the next day boundary so that the PATH samples are taken at
+ * exactly the commits at which the reference takes them.
+ *
+ * usage: gravity_headless (--scenario FILE | --plummer N [--seed S])
+ *            [--steps K] [--dt SECONDS] [--gpus P] [--kernel auto|tiled|strict]
+ *            [--checkpoint K1,K2,...] [--no-path] [--quiet]
+ * prints one JSON line per checkpoint (body state as C99 hex floats) and a
+ * final timing line.
+ */
+#include "gravity_cuda.h"
+#include "gravity_host.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define MAX_PATH_SAMPLES (260 * 365 + 260 / 4) /* MAX_PATH, sim_gravity.c:38 */
+#define YEAR_SECS (365.25 * 86400)
+
+typedef struct { double x, y; } path_point_t;
+
+static uint64_t microsec_now(void) /* CLOCK_MONOTONIC, as util.c:1635-1641 */
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000 + (uint64_t)ts.tv_nsec / 1000;
+}
+
+static void dump_state(const char *label, long long steps, const gravity_scenario_t *s)
+{
+    int i;
+    printf("{\"scenario\": \"%s\", \"steps\": %lld, \"sim_time\": %lld, \"dt\": %d, \"n\": %d, \"bodies\": [",
+           label, steps, (long long)s->sim_time, s->dt, s->n);
+    for (i = 0; i < s->n; i++) {
+        printf("%s{\"name\": \"%s\", \"mass\": \"%a\", \"x\": \"%a\", \"y\": \"%a\", \"vx\": \"%a\", \"vy\": \"%a\"}",
+               i ? ", " : "", s->name[i], s->mass[i], s->x[i], s->y[i], s->vx[i], s->vy[i]);
+    }
+    printf("]}\n");
+    fflush(stdout);
+}
+
+static int usage(const char *argv0)
+{
+    fprintf(stderr,
+            "usage: %s (--scenario FILE | --plummer N [--seed S]) [--steps K] [--dt SEC] [--gpus P]\n"
+            "          [--kernel auto|tiled|strict] [--checkpoint K1,K2,...] [--no-path] [--quiet]\n",
+            argv0);
+    return 2;
+}
+
+int main(int argc, char **argv)
+{
+    const char *scenario_file = NULL, *checkpoints = NULL, *kernel = "auto";
+    long long plummer_n = 0, steps = 1000, seed = 1, done = 0, next_cp;
+    int dt_override = 0, gpus = 1, quiet = 0, want_path = 1, a, i;
+    gravity_scenario_t *sim = NULL;
+    gravity_cuda_t *h = NULL;
+    path_point_t *path = NULL;
+    long long path_tail = 0;
+    int32_t last_day = 0; /* function-static in the reference, starts at 0 */
+    uint64_t t0, t1;
+    char *cp_cursor = NULL;
+
+    for (a = 1; a < argc; a++) {
+        if (!strcmp(argv[a], "--scenario") && a + 1 < argc) scenario_file = argv[++a];
+        else if (!strcmp(argv[a], "--plummer") && a + 1 < argc) plummer_n = atoll(argv[++a]);
+        else if (!strcmp(argv[a], "--seed") && a + 1 < argc) seed = atoll(argv[++a]);
+        else if (!strcmp(argv[a], "--steps") && a + 1 < argc) steps = atoll(argv[++a]);
+        else if (!strcmp(argv[a], "--dt") && a + 1 < argc) dt_override = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--gpus") && a + 1 < argc) gpus = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--kernel") && a + 1 < argc) kernel = argv[++a];
+        else if (!strcmp(argv[a], "--checkpoint") && a + 1 < argc) checkpoints = argv[++a];
+        else if (!strcmp(argv[a], "--no-path")) want_path = 0;
+        else if (!strcmp(argv[a], "--quiet")) quiet = 1;
+        else return usage(argv[0]);
+    }
+    if ((scenario_file == NULL) == (plummer_n == 0)) return usage(argv[0]);
+
+    /* ---- initial conditions (sim_gravity_init) ---- */
+    if (scenario_file) {
+        if (gravity_scenario_load(scenario_file, &sim) != 0) {
+            fprintf(stderr, "ERROR %s '%s' '%s'\n", sim ? sim->error_str[0] : "Out Of Memory",
+                    sim ? sim->error_str[1] : "", sim ? sim->error_str[2] : "");
+            gravity_scenario_free(sim);
+            return 1;
+        }
+    } else {
+        sim = calloc(1, sizeof(*sim));
+        sim->n = (int32_t)plummer_n;
+        sim->dt = 1;
+        sim->sim_width = 50 * GRAVITY_AU;
+        snprintf(sim->sim_name, sizeof(sim->sim_name), "PLUMMER_%lld", plummer_n);
+        sim->mass = calloc((size_t)plummer_n * 6, sizeof(double));
+        sim->radius = sim->mass + plummer_n;
+        sim->x = sim->radius + plummer_n;
+        sim->y = sim->x + plummer_n;
+        sim->vx = sim->y + plummer_n;
+        sim->vy = sim->vx + plummer_n;
+        sim->name = calloc((size_t)plummer_n, GRAVITY_MAX_NAME);
+        sim->disp_color = calloc((size_t)plummer_n * 2, sizeof(int32_t));
+        sim->max_path_disp_dflt = sim->disp_color + plummer_n;
+        if (gravity_plummer_generate(plummer_n, (uint64_t)seed, sim->mass, sim->x, sim->y, sim->vx, sim->vy) != 0) {
+            fprintf(stderr, "ERROR plummer generator failed\n");
+            return 1;
+        }
+    }
+    if (dt_override > 0) sim->dt = dt_override;
+
+    /* ---- the GPU replaces the worker pool (sim_gravity.c:425-442) ---- */
+    if (gravity_cuda_create(&h, sim->n, gpus) != 0) {
+        fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(NULL));
+        return 1;
+    }
+    if (strcmp(kernel, "auto") != 0) {
+        if (gravity_cuda_set_option(h, "kernel", !strcmp(kernel, "tiled") ? GRAVITY_CUDA_KERNEL_TILED
+                                                                           : GRAVITY_CUDA_KERNEL_STRICT) != 0) {
+            fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+            return 1;
+        }
+    }
+    if (gravity_cuda_upload(h, sim->mass, sim->x, sim->y, sim->vx, sim->vy) != 0) {
+        fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+        return 1;
+    }
+    if (want_path && sim->n <= GRAVITY_MAX_OBJECT) {
+        path = calloc((size_t)sim->n * MAX_PATH_SAMPLES, sizeof(path_point_t));
+    }
+
+    if (checkpoints) cp_cursor = strdup(checkpoints);
+    next_cp = -1;
+    if (cp_cursor) {
+        char *tok = strtok(cp_cursor, ",");
+        next_cp = tok ? atoll(tok) : -1;
+        if (next_cp == 0) {
+            dump_state(sim->sim_name, 0, sim);
+            tok = strtok(NULL, ",");
+            next_cp = tok ? atoll(tok) : -1;
+        }
+    }
+
+    /* ---- STATE_RUN ---- */
+    t0 = microsec_now();
+    while (done < steps) {
+        long long batch = steps - done;
+        long long to_sample = gravity_steps_until_day_change(sim->sim_time, sim->dt, last_day);
+        int sample = 0;
+        if (path && to_sample <= batch) {
+            batch = to_sample;
+            sample = 1;
+        }
+        if (next_cp > done && next_cp - done < batch) {
+            batch = next_cp - done;
+            sample = 0;
+        }
+        if (gravity_cuda_step(h, sim->dt, batch) != 0) {
+            fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+            return 1;
+        }
+        /* commit bookkeeping of thread 0 (sim_gravity.c:1229-1260) for the batch */
+        if (sample) {
+            if (gravity_cuda_download(h, sim->x, sim->y, NULL, NULL) != 0) return 1;
+            for (i = 0; i < sim->n; i++) {
+                path[(size_t)i * MAX_PATH_SAMPLES + path_tail % MAX_PATH_SAMPLES].x = sim->x[i];
+                path[(size_t)i * MAX_PATH_SAMPLES + path_tail % MAX_PATH_SAMPLES].y = sim->y[i];
+            }
+            last_day = (int32_t)((sim->sim_time + (batch - 1) * (long long)sim->dt) / 86400);
+            path_tail++;
+        }
+        sim->sim_time += (long long)sim->dt * batch;
+        done += batch;
+        if (done == next_cp) {
+            char *tok;
+            if (gravity_cuda_download(h, sim->x, sim->y, sim->vx, sim->vy) != 0) return 1;
+            dump_state(sim->sim_name, done, sim);
+            tok = strtok(NULL, ",");
+            next_cp = tok ? atoll(tok) : -1;
+        }
+    }
+    t1 = microsec_now();
+
+    if (!quiet) {
+        double secs = (double)(t1 - t0) / 1e6;
+        double kin = 0, pot = 0;
+        long long launches = 0;
+        gravity_cuda_energy(h, &kin, &pot);
+        gravity_cuda_launch_count(h, (int64_t *)&launches);
+        printf("{\"summary\": \"%s\", \"n\": %d, \"steps\": %lld, \"dt\": %d, \"gpus\": %d, \"wall_s\": %.6f, "
+               "\"pairs_per_s\": %.6g, \"rate_years_per_s\": %.6g, \"path_samples\": %lld, "
+               "\"kinetic\": \"%a\", \"potential\": \"%a\", \"kernel_launches\": %lld}\n",
+               sim->sim_name, sim->n, done, sim->dt, gpus, secs,
+               secs > 0 ? (double)sim->n * (sim->n - 1) * (double)done / secs : 0.0,
+               secs > 0 ? (double)sim->dt * (double)done / YEAR_SECS / secs : 0.0, path_tail, kin, pot, launches);
+    }
+
+    gravity_cuda_destroy(h);
+    free(path);
+    free(cp_cursor);
+    gravity_scenario_free(sim);
+    return 0;
+}

@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C ABI of libgravity_cuda) against the
+pinned oracle and the golden fixtures.  Everything here needs a B200.
+
+Bars (BASELINE.json north_star):
+  * STRICT kernels: bit-identical to the reference;
+  * TILED kernel: per-step accelerations <= 1e-12 relative, trajectories
+    <= 1e-9 relative after 10^4 steps on the non-chaotic scenarios, energy
+    drift within the same tolerance.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import proj_entropy_b200 as g
+from conftest import assert_accel_parity, bits_equal, load_fixture, ok_fixture_names, rel_err_rows
+from oracle import oracle_py as oracle
+
+pytestmark = pytest.mark.gpu
+
+ACCEL_TOL = 1e-12
+TRAJ_TOL = 1e-9
+NTHREADS = 16
+
+
+def state0(fx):
+    cp = fx["checkpoints"][0]
+    return fx["mass_f"], cp["x_f"], cp["y_f"], cp["vx_f"], cp["vy_f"]
+
+
+# ---------------------------------------------------------------------------
+# STRICT: bit-identical to the unmodified reference
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ok_fixture_names())
+def test_strict_small_kernel_reproduces_reference_bits(name):
+    """All scenarios, every checkpoint, including 10^5 steps of
+    solar_system_and_rogue_star (BASELINE.json configs[1])."""
+    fx = load_fixture(name)
+    with g.GravityCuda(fx["n"]) as h:            # AUTO -> STRICT for N <= 1024
+        h.upload(*state0(fx))
+        done = 0
+        for cp in fx["checkpoints"][1:]:
+            h.step(fx["dt"], cp["steps"] - done)
+            done = cp["steps"]
+            x, y, vx, vy = h.download()
+            for got, key in ((x, "x_f"), (y, "y_f"), (vx, "vx_f"), (vy, "vy_f")):
+                assert bits_equal(got, cp[key]), "%s step %d %s" % (name, done, key)
+
+
+@pytest.mark.parametrize("n", [1, 2, 129, 1500, 3000])
+def test_strict_rows_kernel_bits_vs_oracle(n):
+    m, x, y, vx, vy = g.plummer(n, seed=3)
+    with g.GravityCuda(n, kernel=g.KERNEL_STRICT) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(7)
+        rax, ray = oracle.accel(m, x, y, vx, vy, 7, nthreads=NTHREADS)
+        assert bits_equal(ax, rax) and bits_equal(ay, ray)
+        h.step(7, 3)
+        got = h.download()
+    want = oracle.step(m, x, y, vx, vy, 7, 3, nthreads=NTHREADS)
+    for a, b in zip(got, want):
+        assert bits_equal(a, b)
+
+
+# ---------------------------------------------------------------------------
+# TILED: tolerance parity
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ok_fixture_names())
+def test_tiled_accel_on_scenarios(name):
+    fx = load_fixture(name)
+    m, x, y, vx, vy = state0(fx)
+    with g.GravityCuda(fx["n"], kernel=g.KERNEL_TILED) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(fx["dt"])
+    rax, ray = oracle.accel(m, x, y, vx, vy, fx["dt"])
+    assert rel_err_rows(ax, ay, rax, ray).max() <= ACCEL_TOL
+
+
+NON_CHAOTIC = ["ref_two_body_circular", "ref_two_body_elliptical", "ref_solar_system",
+               "ref_solar_system_and_rogue_star", "ref_gravity_boost"]
+
+
+@pytest.mark.parametrize("name", NON_CHAOTIC)
+def test_tiled_trajectory_1e4_steps(name):
+    """Trajectories <= 1e-9 relative after 10^4 steps; three_body is excluded
+    because the reference itself calls it chaotic (sim_gravity_help.h:63-65)."""
+    fx = load_fixture(name)
+    cp = [c for c in fx["checkpoints"] if c["steps"] == 10000][0]
+    with g.GravityCuda(fx["n"], kernel=g.KERNEL_TILED) as h:
+        h.upload(*state0(fx))
+        h.step(fx["dt"], 10000)
+        x, y, vx, vy = h.download()
+    # positions: relative to the size of the system; velocities: per body
+    scale = np.hypot(cp["x_f"], cp["y_f"]).max()
+    assert (np.hypot(x - cp["x_f"], y - cp["y_f"]) / scale).max() <= TRAJ_TOL
+    vscale = np.hypot(cp["vx_f"], cp["vy_f"]).max()
+    assert (np.hypot(vx - cp["vx_f"], vy - cp["vy_f"]) / vscale).max() <= TRAJ_TOL
+    per_body = np.hypot(x - cp["x_f"], y - cp["y_f"]) / np.maximum(np.hypot(cp["x_f"], cp["y_f"]), 1e-300)
+    assert np.median(per_body) <= TRAJ_TOL
+
+
+def test_tiled_rogue_star_1e5_steps_and_energy_drift():
+    """BASELINE.json configs[1]: 10^5 steps, checked every 10^4th step against
+    the reference, energy-drift curve within the same tolerance."""
+    fx = load_fixture("ref_solar_system_and_rogue_star")
+    m = fx["mass_f"]
+    cps = [c for c in fx["checkpoints"] if c["steps"] % 10000 == 0 and c["steps"] > 0]
+    e0 = sum(oracle.energy(*state0(fx)))
+    with g.GravityCuda(fx["n"], kernel=g.KERNEL_TILED) as h:
+        h.upload(*state0(fx))
+        done = 0
+        for cp in cps:
+            h.step(fx["dt"], cp["steps"] - done)
+            done = cp["steps"]
+            x, y, vx, vy = h.download()
+            scale = np.hypot(cp["x_f"], cp["y_f"]).max()
+            assert (np.hypot(x - cp["x_f"], y - cp["y_f"]) / scale).max() <= TRAJ_TOL, done
+            drift_ref = (sum(oracle.energy(m, cp["x_f"], cp["y_f"], cp["vx_f"], cp["vy_f"])) - e0) / abs(e0)
+            ke, pe = h.energy()
+            drift_gpu = (ke + pe - e0) / abs(e0)
+            assert abs(drift_gpu - drift_ref) <= TRAJ_TOL, done
+
+
+@pytest.mark.parametrize("n", [1025, 1300, 4096, 4097, 20000])
+def test_tiled_accel_plummer_ragged_sizes(n):
+    m, x, y, vx, vy = g.plummer(n, seed=1)
+    with g.GravityCuda(n, kernel=g.KERNEL_TILED) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(1)
+    rax, ray = oracle.accel(m, x, y, vx, vy, 1, nthreads=NTHREADS)
+    assert_accel_parity(ax, ay, rax, ray, (m, x, y, vx, vy), 1)
+
+
+@pytest.mark.parametrize("threads,bpt,cps", [(128, 1, 4), (128, 2, 3), (128, 4, 2), (256, 1, 2), (256, 2, 2), (256, 4, 1)])
+def test_tiled_kernel_shapes_agree(threads, bpt, cps):
+    n = 6000
+    m, x, y, vx, vy = g.plummer(n, seed=5)
+    with g.GravityCuda(n, kernel=g.KERNEL_TILED, threads=threads, bodies_per_thread=bpt, ctas_per_sm=cps) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(3)
+        h.step(3, 2)
+        got = h.download()
+    rax, ray = oracle.accel(m, x, y, vx, vy, 3, nthreads=NTHREADS)
+    assert_accel_parity(ax, ay, rax, ray, (m, x, y, vx, vy), 3)
+    want = oracle.step(m, x, y, vx, vy, 3, 2, nthreads=NTHREADS)
+    for a, b in zip(got, want):
+        assert np.allclose(a, b, rtol=1e-11, atol=0)
+
+
+def test_tiled_accel_config3_full_65536():
+    """BASELINE.json configs[2]: N = 65,536 on one GPU, accelerations against the
+    oracle on the full set (4.3e9 pairs on the host)."""
+    n = 65536
+    m, x, y, vx, vy = g.plummer(n, seed=1)
+    with g.GravityCuda(n) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(1)
+    rax, ray = oracle.accel(m, x, y, vx, vy, 1, nthreads=NTHREADS)
+    err = assert_accel_parity(ax, ay, rax, ray, (m, x, y, vx, vy), 1)
+    assert np.median(err) <= 1e-14
+    # and no farther from a long-double evaluation than the reference itself is
+    rows = np.arange(0, n, 64, dtype=np.int64)
+    tax, tay = oracle.accel_ld(m, x, y, vx, vy, 1, rows=rows, nthreads=NTHREADS)
+    e_gpu = rel_err_rows(ax[rows], ay[rows], tax, tay)
+    e_ref = rel_err_rows(rax[rows], ray[rows], tax, tay)
+    assert np.median(e_gpu) <= 2 * np.median(e_ref) + 1e-16
+
+
+def test_tiled_coincident_bodies_take_the_guarded_path():
+    """Exactly coincident pairs are skipped (sim_gravity.c:1199-1201); the fast
+    loop poisons those bodies with NaN and the commit kernel repairs them."""
+    n = 5000
+    m, x, y, vx, vy = g.plummer(n, seed=9)
+    for a, b in ((10, 4000), (11, 12), (2999, 3000)):
+        x[b], y[b] = x[a], y[a]
+        vx[a] = vy[a] = 0.0        # a's half-drifted position is then exactly b's position
+    with g.GravityCuda(n, kernel=g.KERNEL_TILED) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(2)
+        h.step(2, 1)
+        got = h.download()
+    assert np.isfinite(ax).all() and np.isfinite(ay).all()
+    rax, ray = oracle.accel(m, x, y, vx, vy, 2, nthreads=NTHREADS)
+    assert_accel_parity(ax, ay, rax, ray, (m, x, y, vx, vy), 2)
+    want = oracle.step(m, x, y, vx, vy, 2, 1, nthreads=NTHREADS)
+    for a, b in zip(got, want):
+        assert np.allclose(a, b, rtol=1e-11, atol=0)
+
+
+def test_self_term_is_skipped_by_index_not_by_distance():
+    """Only the i-body is half-drifted (sim_gravity.c:1186-1197), so the self
+    distance is |V*DT/2| != 0; a kernel that relied on r == 0 would add a huge
+    bogus self-force.  Big DT and big velocities make that visible."""
+    n = 2048
+    m, x, y, vx, vy = g.plummer(n, seed=2)
+    with g.GravityCuda(n, kernel=g.KERNEL_TILED) as h:
+        h.upload(m, x, y, vx * 50, vy * 50)
+        ax, ay = h.accel(86400)
+    rax, ray = oracle.accel(m, x, y, vx * 50, vy * 50, 86400, nthreads=NTHREADS)
+    assert_accel_parity(ax, ay, rax, ray, (m, x, y, vx * 50, vy * 50), 86400)
+
+
+def test_energy_matches_oracle():
+    n = 10000
+    m, x, y, vx, vy = g.plummer(n, seed=4)
+    with g.GravityCuda(n) as h:
+        h.upload(m, x, y, vx, vy)
+        ke, pe = h.energy()
+    rke, rpe = oracle.energy(m, x, y, vx, vy, nthreads=NTHREADS)
+    assert abs(ke - rke) / rke < 1e-13
+    assert abs(pe - rpe) / abs(rpe) < 1e-12
+
+
+def test_step_objects_aos_adapter():
+    """The reference keeps bodies as individually allocated object_t records
+    (X@32, Y@40, VX@48, VY@56, MASS@64; sim_gravity.c:83-105)."""
+    fx = load_fixture("ref_gravity_boost")
+    m, x, y, vx, vy = state0(fx)
+    n = fx["n"]
+    recs = [ctypes.create_string_buffer(256) for _ in range(n)]
+    for i, r in enumerate(recs):
+        for off, v in ((32, x[i]), (40, y[i]), (48, vx[i]), (56, vy[i]), (64, m[i])):
+            ctypes.c_double.from_buffer(r, off).value = v
+    with g.GravityCuda(n) as h:
+        h.step_objects([ctypes.addressof(r) for r in recs], 32, 40, 48, 56, 64, fx["dt"], 100)
+    cp = [c for c in fx["checkpoints"] if c["steps"] == 100][0]
+    got = np.array([[ctypes.c_double.from_buffer(r, off).value for off in (32, 40, 48, 56)] for r in recs])
+    assert bits_equal(got[:, 0], cp["x_f"]) and bits_equal(got[:, 3], cp["vy_f"])
+
+
+def test_error_behaviour():
+    with pytest.raises(g.GravityError):
+        g.GravityCuda(0)
+    with g.GravityCuda(4) as h:
+        with pytest.raises(g.GravityError, match="before upload"):
+            h.step(1, 1)
+        with pytest.raises(g.GravityError, match="unknown option"):
+            h.set_option("nonsense", 1)
+
+
+# ---------------------------------------------------------------------------
+# Size-independent properties at BASELINE.json's full size
+# ---------------------------------------------------------------------------
+
+def test_full_size_1m_properties_and_row_sample():
+    n = 1 << 20
+    m, x, y, vx, vy = g.plummer(n, seed=1)
+    zero = np.zeros(n)
+    with g.GravityCuda(n) as h:
+        # with V = 0 nothing is drifted, pair forces are antisymmetric and the
+        # total force must vanish to rounding
+        h.upload(m, x, y, zero, zero)
+        ax, ay = h.accel(1)
+        assert np.isfinite(ax).all() and np.isfinite(ay).all()
+        fsum = np.hypot(np.sum(m * ax), np.sum(m * ay))
+        assert fsum / np.sum(m * np.hypot(ax, ay)) < 1e-9
+        # row sample against the oracle (1,024 rows x 1M bodies on the host)
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(1)
+        rows = np.arange(0, n, 1024, dtype=np.int64)
+        rax, ray = oracle.accel(m, x, y, vx, vy, 1, rows=rows, nthreads=NTHREADS)
+        pure = rel_err_rows(ax[rows], ay[rows], rax, ray)
+        floor = 0.1 * np.median(np.hypot(rax, ray))
+        assert (np.hypot(ax[rows] - rax, ay[rows] - ray) / np.maximum(np.hypot(rax, ray), floor)).max() <= ACCEL_TOL
+        assert (pure > ACCEL_TOL).sum() <= 1 and np.median(pure) <= 2e-14
+        # one step moves every body by V*DT + A*DT^2/2 (sim_gravity.c:1213-1219)
+        h.step(1, 1)
+        nx, ny, nvx, nvy = h.download()
+        assert np.allclose(nx[rows], x[rows] + (vx[rows] + 0.5 * rax), rtol=1e-13, atol=0)
+        assert np.allclose(nvy[rows], vy[rows] + ray, rtol=1e-12, atol=0)
+
+
+# ---------------------------------------------------------------------------
+# Multi-GPU (single-process handle; skipped on a one-GPU box)
+# ---------------------------------------------------------------------------
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_two_gpus_agree_with_one(gpu_count, overlap):
+    if gpu_count < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 30000
+    m, x, y, vx, vy = g.plummer(n, seed=6)
+    with g.GravityCuda(n, ngpus=1, kernel=g.KERNEL_TILED) as h1:
+        h1.upload(m, x, y, vx, vy)
+        h1.step(5, 4)
+        one = h1.download()
+    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_TILED, overlap=overlap) as h2:
+        h2.upload(m, x, y, vx, vy)
+        h2.step(5, 4)
+        two = h2.download()
+    for a, b in zip(one, two):
+        assert np.allclose(a, b, rtol=1e-12, atol=0)
+    want = oracle.step(m, x, y, vx, vy, 5, 4, nthreads=NTHREADS)
+    for a, b in zip(two, want):
+        assert np.allclose(a, b, rtol=1e-11, atol=0)
+
+
+@pytest.mark.multigpu
+def test_two_gpus_strict_is_still_bit_exact(gpu_count):
+    if gpu_count < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 1500
+    m, x, y, vx, vy = g.plummer(n, seed=8)
+    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_STRICT) as h:
+        h.upload(m, x, y, vx, vy)
+        h.step(9, 3)
+        got = h.download()
+    want = oracle.step(m, x, y, vx, vy, 9, 3, nthreads=NTHREADS)
+    for a, b in zip(got, want):
+        assert bits_equal(a, b)
