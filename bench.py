@@ -194,40 +194,16 @@ def run_ours(args, rank, world, local_rank):
 
     if g.device_count() < 1:
         raise SystemExit("bench.py: no sm_100 GPU visible; libgravity_cuda has no CPU fallback")
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from proj_entropy_b200.dist import Ranks
+    ranks = Ranks("nccl")
     n = args.bodies
     state = g.plummer(n, seed=1)           # identical bytes on every rank
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
 
     # the library's own NCCL communicator: id made on rank 0, broadcast by torch
     nccl_id = None
     if world > 1:
-        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(g.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+        nccl_id = ranks.broadcast_bytes(g.nccl_unique_id() if rank == 0 else None, 128)
 
     opts = {"kernel": g.KERNEL_TILED, "overlap": args.overlap}
     if args.threads:
@@ -337,9 +313,7 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     sampler.stop()
     h.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    ranks.close()
 
 
 def main():

@@ -37,6 +37,7 @@ struct DeviceCtx {
     double  *mass = nullptr;
     double2 *vel = nullptr;
     double2 *accel = nullptr;
+    double  *stage = nullptr;      // 4 x npad doubles: SoA staging for upload / download
     double  *kin = nullptr, *pot = nullptr;
     double2 *partial = nullptr;
     Segment *seg = nullptr;
@@ -74,7 +75,6 @@ struct gravity_cuda {
     int64_t launches = 0;
     bool timing = false;
     int64_t hot_launches = 0;
-    std::vector<double> host_stage;  // staging for AoS adapter / download
     char err[200] = "";
 };
 
@@ -432,6 +432,7 @@ int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
     CUDA_TRY(h, cudaMalloc(&c.mass, sizeof(double) * h->npad));
     CUDA_TRY(h, cudaMalloc(&c.vel, sizeof(double2) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.accel, sizeof(double2) * h->chunk));
+    CUDA_TRY(h, cudaMalloc(&c.stage, sizeof(double) * 4 * h->npad));
     CUDA_TRY(h, cudaMalloc(&c.kin, sizeof(double) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.pot, sizeof(double) * h->chunk));
     CUDA_TRY(h, cudaMemsetAsync(c.vel, 0, sizeof(double2) * h->chunk, c.stream));
@@ -572,7 +573,7 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
         if (c.comm_stream) cudaStreamSynchronize(c.comm_stream);
         if (c.comm) ncclCommDestroy(c.comm);
         cudaFree(c.pos[0]); cudaFree(c.pos[1]); cudaFree(c.mass); cudaFree(c.vel); cudaFree(c.accel);
-        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.partial); cudaFree(c.seg);
+        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.partial); cudaFree(c.seg);
         cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin);
         for (cudaEvent_t e : c.kev) cudaEventDestroy(e);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
@@ -615,25 +616,23 @@ int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, 
     if (!h) return fail(nullptr, "upload: NULL handle");
     if (!mass || !x || !y || !vx || !vy) return fail(h, "upload: NULL array");
     if (sync_all(h) != 0) return -1;
-    const int64_t n = h->n;
-    std::vector<double> &st = h->host_stage;
-    st.resize((size_t)4 * n);
-    double *pxy = st.data();            // interleaved {x,y}
-    double *vxy = st.data() + 2 * n;    // interleaved {vx,vy}
-    for (int64_t i = 0; i < n; ++i) {
-        pxy[2 * i] = x[i];
-        pxy[2 * i + 1] = y[i];
-        vxy[2 * i] = vx[i];
-        vxy[2 * i + 1] = vy[i];
-    }
+    const int64_t n = h->n, np = h->npad;
     h->cur = 0;
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
-        CUDA_TRY(h, cudaMemcpyAsync(c.pos[0], pxy, sizeof(double2) * n, cudaMemcpyHostToDevice, c.stream));
+        double *sx = c.stage, *sy = c.stage + np, *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
+        CUDA_TRY(h, cudaMemcpyAsync(sx, x, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(h, cudaMemcpyAsync(sy, y, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
         CUDA_TRY(h, cudaMemcpyAsync(c.mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
-        if (c.n_local > 0)
-            CUDA_TRY(h, cudaMemcpyAsync(c.vel, vxy + 2 * c.i0, sizeof(double2) * c.n_local,
-                                        cudaMemcpyHostToDevice, c.stream));
+        k_pack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(sx, sy, c.pos[0], n);
+        h->launches++;
+        if (c.n_local > 0) {
+            CUDA_TRY(h, cudaMemcpyAsync(svx, vx + c.i0, sizeof(double) * c.n_local, cudaMemcpyHostToDevice, c.stream));
+            CUDA_TRY(h, cudaMemcpyAsync(svy, vy + c.i0, sizeof(double) * c.n_local, cudaMemcpyHostToDevice, c.stream));
+            k_pack_pairs<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(svx, svy, c.vel, c.n_local);
+            h->launches++;
+        }
+        CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaEventRecord(c.ev_gather, c.stream));
     }
     if (sync_all(h) != 0) return -1;
@@ -646,51 +645,50 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
     if (!h) return fail(nullptr, "download: NULL handle");
     if (!h->uploaded) return fail(h, "download before upload");
     if (join_comm(h) != 0 || sync_all(h) != 0) return -1;
-    const int64_t n = h->n;
-    std::vector<double> &st = h->host_stage;
-    st.resize((size_t)4 * n);
-    double *pxy = st.data();
-    double *vxy = st.data() + 2 * n;
+    const int64_t n = h->n, np = h->npad;
     if (x || y) {
         DeviceCtx &c = h->ctx[0];
         CUDA_TRY(h, cudaSetDevice(c.device));
-        CUDA_TRY(h, cudaMemcpy(pxy, c.pos[h->cur], sizeof(double2) * n, cudaMemcpyDeviceToHost));
-        for (int64_t i = 0; i < n; ++i) {
-            if (x) x[i] = pxy[2 * i];
-            if (y) y[i] = pxy[2 * i + 1];
-        }
+        double *sx = c.stage, *sy = c.stage + np;
+        k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(c.pos[h->cur], sx, sy, n);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        if (x) CUDA_TRY(h, cudaMemcpyAsync(x, sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+        if (y) CUDA_TRY(h, cudaMemcpyAsync(y, sy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
     }
     if (vx || vy) {
-        if (h->single_process) {
+        if (h->single_process || h->nranks == 1) {
             for (DeviceCtx &c : h->ctx) {
                 if (c.n_local == 0) continue;
                 CUDA_TRY(h, cudaSetDevice(c.device));
-                CUDA_TRY(h, cudaMemcpy(vxy + 2 * c.i0, c.vel, sizeof(double2) * c.n_local, cudaMemcpyDeviceToHost));
+                double *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
+                k_unpack_pairs<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(c.vel, svx, svy, c.n_local);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+                if (vx) CUDA_TRY(h, cudaMemcpyAsync(vx + c.i0, svx, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
+                if (vy) CUDA_TRY(h, cudaMemcpyAsync(vy + c.i0, svy, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
             }
-        } else if (h->nranks == 1) {
-            DeviceCtx &c = h->ctx[0];
-            CUDA_TRY(h, cudaMemcpy(vxy, c.vel, sizeof(double2) * c.n_local, cudaMemcpyDeviceToHost));
         } else {
             // rank mode: gather the velocity shards through the spare position buffer
             DeviceCtx &c = h->ctx[0];
             CUDA_TRY(h, cudaSetDevice(c.device));
             double2 *tmp = c.pos[h->cur ^ 1];
+            double *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
             CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.vel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
             NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
-            CUDA_TRY(h, cudaMemcpyAsync(vxy, tmp, sizeof(double2) * n, cudaMemcpyDeviceToHost, c.stream));
+            k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(tmp, svx, svy, n);
+            h->launches++;
             // restore the padding the gather overwrote with velocity padding (zeros)
             const int64_t npadding = h->npad - h->n;
             if (npadding > 0) {
                 k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(tmp, tmp, c.mass, h->n, h->npad);
             }
-            CUDA_TRY(h, cudaStreamSynchronize(c.stream));
-        }
-        for (int64_t i = 0; i < n; ++i) {
-            if (vx) vx[i] = vxy[2 * i];
-            if (vy) vy[i] = vxy[2 * i + 1];
+            CUDA_TRY(h, cudaGetLastError());
+            if (vx) CUDA_TRY(h, cudaMemcpyAsync(vx, svx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+            if (vy) CUDA_TRY(h, cudaMemcpyAsync(vy, svy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
         }
     }
-    return 0;
+    return sync_all(h);
 }
 
 int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
@@ -742,34 +740,36 @@ int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay)
     if (join_comm(h) != 0) return -1;
     if (enqueue_evaluation(h, (double)dt, true, false) != 0) return -1;
     if (sync_all(h) != 0) return -1;
-    const int64_t n = h->n;
-    std::vector<double> &st = h->host_stage;
-    st.resize((size_t)4 * n);
-    double *axy = st.data();
+    const int64_t n = h->n, np = h->npad;
     if (h->single_process || h->nranks == 1) {
         for (DeviceCtx &c : h->ctx) {
             if (c.n_local == 0) continue;
             CUDA_TRY(h, cudaSetDevice(c.device));
-            CUDA_TRY(h, cudaMemcpy(axy + 2 * c.i0, c.accel, sizeof(double2) * c.n_local, cudaMemcpyDeviceToHost));
+            double *sx = c.stage, *sy = c.stage + np;
+            k_unpack_pairs<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(c.accel, sx, sy, c.n_local);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+            CUDA_TRY(h, cudaMemcpyAsync(ax + c.i0, sx, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
+            CUDA_TRY(h, cudaMemcpyAsync(ay + c.i0, sy, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
         }
     } else {
         DeviceCtx &c = h->ctx[0];
         CUDA_TRY(h, cudaSetDevice(c.device));
         double2 *tmp = c.pos[h->cur ^ 1];
+        double *sx = c.stage, *sy = c.stage + np;
         CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.accel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
         NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
-        CUDA_TRY(h, cudaMemcpyAsync(axy, tmp, sizeof(double2) * n, cudaMemcpyDeviceToHost, c.stream));
+        k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(tmp, sx, sy, n);
+        h->launches++;
         const int64_t npadding = h->npad - h->n;
         if (npadding > 0) {
             k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(tmp, tmp, c.mass, h->n, h->npad);
         }
-        CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaMemcpyAsync(ax, sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(h, cudaMemcpyAsync(ay, sy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
     }
-    for (int64_t i = 0; i < n; ++i) {
-        ax[i] = axy[2 * i];
-        ay[i] = axy[2 * i + 1];
-    }
-    return 0;
+    return sync_all(h);
 }
 
 int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size_t off_x, size_t off_y,

@@ -208,8 +208,8 @@ __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, con
                 // is |V*DT/2|, not 0, because only the i-body is drifted.
                 w = (gj0 + j == gi[r]) ? 0.0 : w;
             }
-            ax[r] = fma(w, dx, ax[r]);
-            ay[r] = fma(w, dy, ay[r]);
+            ax[r] = fma(w, dx, ax[r]);                   // sim_gravity.c:1203
+            ay[r] = fma(w, dy, ay[r]);                   // sim_gravity.c:1204
         }
     }
 }
@@ -583,6 +583,25 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, doub
     // the warp arbiter lets some CTAs of an SM finish long before others; the
     // longest-lived thread spans the whole kernel
     if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long *)cycles, (unsigned long long)(t1 - t0));
+}
+
+// Host SoA <-> device interleaved layout (upload / download): the host arrays
+// are copied as they are and (de)interleaved here, so the host never loops over
+// the bodies and pinned host buffers stream at full PCIe speed.
+__global__ void k_pack_pairs(const double *__restrict__ a, const double *__restrict__ b, double2 *dst, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_double2(a[i], b[i]);
+}
+
+__global__ void k_unpack_pairs(const double2 *__restrict__ src, double *a, double *b, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double2 v = src[i];
+        a[i] = v.x;
+        b[i] = v.y;
+    }
 }
 
 // Parks padding bodies (global index >= n): mass 0, far away, never updated.

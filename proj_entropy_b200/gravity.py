@@ -28,7 +28,8 @@ def load_cuda_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.path.join(_HERE, "libgravity_cuda.so")
+    # GRAVITY_CUDA_LIB lets developer tools A/B a differently compiled build
+    path = os.environ.get("GRAVITY_CUDA_LIB") or os.path.join(_HERE, "libgravity_cuda.so")
     if not os.path.exists(path):
         raise GravityError("%s is not built (run `make` or __graft_entry__.build()); "
                            "there is no fallback implementation" % path)

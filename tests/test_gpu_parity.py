@@ -311,3 +311,55 @@ def test_two_gpus_strict_is_still_bit_exact(gpu_count):
     want = oracle.step(m, x, y, vx, vy, 9, 3, nthreads=NTHREADS)
     for a, b in zip(got, want):
         assert bits_equal(a, b)
+
+
+# ---------------------------------------------------------------------------
+# The C host: scenario file -> gravity_headless -> state, PATH sampling
+# ---------------------------------------------------------------------------
+
+def _reference_path_samples(steps, dt):
+    """Replay of the commit block (sim_gravity.c:1229-1260): how many PATH
+    samples the reference takes in `steps` steps from sim_time 0."""
+    sim_time, last_day, tail = 0, 0, 0
+    for _ in range(steps):
+        day = sim_time // 86400
+        if day != last_day:
+            tail += 1
+        last_day = day
+        sim_time += dt
+    return tail
+
+
+@pytest.mark.parametrize("name", [n for n in ok_fixture_names("own_")])
+def test_headless_c_driver_matches_reference_bits(name):
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT, scenario_path
+    fx = load_fixture(name)
+    path = scenario_path(fx)
+    steps = [c["steps"] for c in fx["checkpoints"]]
+    exe = os.path.join(ROOT, "proj_entropy_b200", "gravity_headless")
+    p = subprocess.run([exe, "--scenario", path, "--steps", str(steps[-1]),
+                        "--checkpoint", ",".join(str(s) for s in steps)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    states, summary = lines[:-1], lines[-1]
+    assert [s["steps"] for s in states] == steps
+    for s, cp in zip(states, fx["checkpoints"]):
+        assert s["sim_time"] == cp["sim_time"] and s["dt"] == fx["dt"] and s["n"] == fx["n"]
+        for key in ("x", "y", "vx", "vy"):
+            got = [float.fromhex(b[key]) for b in s["bodies"]]
+            assert bits_equal(got, cp[key + "_f"]), "%s step %d %s" % (name, s["steps"], key)
+    assert summary["path_samples"] == _reference_path_samples(steps[-1], fx["dt"])
+
+
+def test_upload_download_round_trip_bits():
+    n = 70001
+    m, x, y, vx, vy = g.plummer(n, seed=11)
+    with g.GravityCuda(n) as h:
+        h.upload(m, x, y, vx, vy)
+        got = h.download()
+    for a, b in zip(got, (x, y, vx, vy)):
+        assert bits_equal(a, b)
