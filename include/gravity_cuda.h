@@ -82,7 +82,10 @@ const char *gravity_cuda_last_error(const gravity_cuda_t *h);
 
 /* Options: "kernel" (GRAVITY_CUDA_KERNEL_*), "threads" (CTA size of the tiled
  * kernel: 128|256), "bodies_per_thread" (1|2|4), "ctas_per_sm" (1..8),
- * "overlap" (0|1: start the local j-shard while the all-gather is in flight).
+ * "overlap" (0|1: start the local j-shard while the all-gather is in flight),
+ * "mass_fold" (0|1, default 1: j-tiles whose 256 masses are bit-identical are
+ * summed without the mass and scaled once per tile -- 12 instead of 13 FP64
+ * instructions per pair; results differ from mass_fold=0 by rounding only).
  * Must be set before the first step/accel after create. */
 int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value);
 

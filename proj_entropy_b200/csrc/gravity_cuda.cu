@@ -37,6 +37,7 @@ struct DeviceCtx {
     double  *mass = nullptr;
     double2 *vel = nullptr;
     double2 *accel = nullptr;
+    double  *tile_mass = nullptr;  // [npad / kTile], see k_tile_mass
     double  *stage = nullptr;      // 4 x npad doubles: SoA staging for upload / download
     double  *kin = nullptr, *pot = nullptr;
     double2 *partial = nullptr;
@@ -71,7 +72,7 @@ struct gravity_cuda {
     int cur = 0;                     // which pos[] holds time t
     bool uploaded = false, planned = false;
     int opt_kernel = GRAVITY_CUDA_KERNEL_AUTO;
-    int opt_threads = 256, opt_bpt = 4, opt_ctas_per_sm = 1, opt_overlap = 0;
+    int opt_threads = 256, opt_bpt = 4, opt_ctas_per_sm = 1, opt_overlap = 0, opt_mass_fold = 1;
     int64_t launches = 0;
     bool timing = false;
     int64_t hot_launches = 0;
@@ -299,6 +300,7 @@ int launch_tiled_phase(gravity_cuda_t *h, DeviceCtx &c, int phase, double dt)
     P.partial = c.partial;
     P.seg = c.seg;
     P.cta_seg_begin = c.cta_seg_begin + ph.cta_seg_offset;
+    P.tile_mass = h->opt_mass_fold ? c.tile_mass : nullptr;
     P.i_global0 = c.i0;
     P.n_local = c.n_local;
     P.dt = dt;
@@ -433,6 +435,7 @@ int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
     CUDA_TRY(h, cudaMalloc(&c.vel, sizeof(double2) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.accel, sizeof(double2) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.stage, sizeof(double) * 4 * h->npad));
+    CUDA_TRY(h, cudaMalloc(&c.tile_mass, sizeof(double) * (h->npad / kTile)));
     CUDA_TRY(h, cudaMalloc(&c.kin, sizeof(double) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.pot, sizeof(double) * h->chunk));
     CUDA_TRY(h, cudaMemsetAsync(c.vel, 0, sizeof(double2) * h->chunk, c.stream));
@@ -573,7 +576,7 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
         if (c.comm_stream) cudaStreamSynchronize(c.comm_stream);
         if (c.comm) ncclCommDestroy(c.comm);
         cudaFree(c.pos[0]); cudaFree(c.pos[1]); cudaFree(c.mass); cudaFree(c.vel); cudaFree(c.accel);
-        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.partial); cudaFree(c.seg);
+        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.tile_mass); cudaFree(c.partial); cudaFree(c.seg);
         cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin);
         for (cudaEvent_t e : c.kev) cudaEventDestroy(e);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
@@ -603,6 +606,8 @@ int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
         h->opt_ctas_per_sm = (int)value;
     } else if (!strcmp(key, "overlap")) {
         h->opt_overlap = value ? 1 : 0;
+    } else if (!strcmp(key, "mass_fold")) {
+        h->opt_mass_fold = value ? 1 : 0;
     } else {
         return fail(h, "unknown option '%s'", key);
     }
@@ -625,7 +630,9 @@ int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, 
         CUDA_TRY(h, cudaMemcpyAsync(sy, y, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
         CUDA_TRY(h, cudaMemcpyAsync(c.mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
         k_pack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(sx, sy, c.pos[0], n);
-        h->launches++;
+        const int n_tile = (int)(np / kTile);
+        k_tile_mass<<<(n_tile + 3) / 4, 128, 0, c.stream>>>(c.mass, c.tile_mass, n_tile);
+        h->launches += 2;
         if (c.n_local > 0) {
             CUDA_TRY(h, cudaMemcpyAsync(svx, vx + c.i0, sizeof(double) * c.n_local, cudaMemcpyHostToDevice, c.stream));
             CUDA_TRY(h, cudaMemcpyAsync(svy, vy + c.i0, sizeof(double) * c.n_local, cudaMemcpyHostToDevice, c.stream));

@@ -40,6 +40,8 @@ struct AccumParams {
     double2       *partial;         // [nseg][IB]
     const Segment *seg;
     const int32_t *cta_seg_begin;   // [gridDim.x + 1]
+    const double  *tile_mass;       // [n_tile] common mass of a j-tile whose 256 masses are
+                                    // bit-identical, NaN otherwise; NULL = never fold
     int64_t        i_global0;       // global index of local body 0
     int64_t        n_local;         // real bodies in the local shard
     double         dt;              // (double)DT
@@ -151,6 +153,21 @@ __device__ __forceinline__ double pair_weight(double dx, double dy, double mj)
     return w0 * g;
 }
 
+// r2^(-3/2) alone, 12 FP64-pipe instructions per pair: used for j-tiles whose
+// bodies all carry the same mass m, where sum_j m*w_j*d_j = m * sum_j w_j*d_j and
+// the multiplication by m moves out of the pair loop (one FMA per tile).
+__device__ __forceinline__ double pair_weight_unit_mass(double dx, double dy)
+{
+    const double r2 = fma(dy, dy, dx * dx);
+    const double y0 = rsqrt_seed(r2);
+    const double b  = y0 * y0;
+    const double e  = fma(-r2, b, 1.0);
+    const double c  = y0 * b;
+    const double p  = fma(1.875, e, 1.5);
+    const double g  = fma(e, p, 1.0);
+    return c * g;
+}
+
 // The same pair exactly as the reference evaluates it (sim_gravity.c:1196-1204):
 // correctly rounded IEEE sqrt and divide, no FMA contraction.
 __device__ __forceinline__ void pair_strict(double xj, double yj, double mj, double px, double py,
@@ -188,7 +205,7 @@ __device__ __forceinline__ void kick_drift(double sum, double dt, double p, doub
 // ring filled by 1-D bulk copies issued by thread 0 and signalled through
 // mbarriers; every lane reads the same j, so the LDS are broadcasts.
 
-template <int THREADS, int R, bool DIAG>
+template <int THREADS, int R, bool DIAG, bool FOLD>
 __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, const double *__restrict__ sm,
                                              const double (&xi)[R], const double (&yi)[R],
                                              double (&ax)[R], double (&ay)[R],
@@ -197,12 +214,12 @@ __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, con
 #pragma unroll 4
     for (int j = 0; j < kTile; ++j) {
         const double2 pj = sp[j];
-        const double  mj = sm[j];
+        const double  mj = FOLD ? 0.0 : sm[j];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double dx = pj.x - xi[r];
             const double dy = pj.y - yi[r];
-            double w = pair_weight(dx, dy, mj);
+            double w = FOLD ? pair_weight_unit_mass(dx, dy) : pair_weight(dx, dy, mj);
             if (DIAG) {
                 // self is skipped by index (sim_gravity.c:1191): its distance
                 // is |V*DT/2|, not 0, because only the i-body is drifted.
@@ -295,14 +312,29 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
 
         for (int t = sg.tile_begin; t < sg.tile_end; ++t) {
             if (tid == 0) issue_next();
+            const double tile_m = P.tile_mass ? __ldg(P.tile_mass + t) : __longlong_as_double(0x7ff8000000000000LL);
             const int stage = consumed % kStages;
             mbar_wait(&s_full[stage], (consumed / kStages) & 1);
 
-            const int64_t gj0 = (int64_t)t * kTile;
-            if (gj0 < gi_hi && gj0 + kTile > gi_lo) {
-                consume_tile<THREADS, R, true>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
+            const int64_t gj0  = (int64_t)t * kTile;
+            const bool    diag = gj0 < gi_hi && gj0 + kTile > gi_lo;
+            if (tile_m == tile_m) {
+                // all 256 masses of this tile are identical: sum without the mass,
+                // fold it in once per tile
+                double sx[R], sy[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) sx[r] = sy[r] = 0.0;
+                if (diag) consume_tile<THREADS, R, true, true>(s_pos[stage], s_mass[stage], xi, yi, sx, sy, gi, gj0);
+                else      consume_tile<THREADS, R, false, true>(s_pos[stage], s_mass[stage], xi, yi, sx, sy, gi, gj0);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    ax[r] = fma(tile_m, sx[r], ax[r]);
+                    ay[r] = fma(tile_m, sy[r], ay[r]);
+                }
+            } else if (diag) {
+                consume_tile<THREADS, R, true, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
             } else {
-                consume_tile<THREADS, R, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
+                consume_tile<THREADS, R, false, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[stage]);
@@ -583,6 +615,21 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *sink, int iters, doub
     // the warp arbiter lets some CTAs of an SM finish long before others; the
     // longest-lived thread spans the whole kernel
     if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long *)cycles, (unsigned long long)(t1 - t0));
+}
+
+// One warp per j-tile: tile_mass[t] = m if all kTile masses of the tile have the
+// same bits, NaN otherwise.
+__global__ void k_tile_mass(const double *__restrict__ mass, double *tile_mass, int n_tile)
+{
+    const int t    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= n_tile) return;
+    const double   *m     = mass + (size_t)t * kTile;
+    const long long first = __double_as_longlong(m[0]);
+    bool same = true;
+    for (int k = lane; k < kTile; k += 32) same = same && (__double_as_longlong(m[k]) == first);
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) tile_mass[t] = same ? m[0] : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // Host SoA <-> device interleaved layout (upload / download): the host arrays

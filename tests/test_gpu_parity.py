@@ -149,6 +149,30 @@ def test_tiled_kernel_shapes_agree(threads, bpt, cps):
         assert np.allclose(a, b, rtol=1e-11, atol=0)
 
 
+@pytest.mark.parametrize("fold", [0, 1])
+def test_mass_fold_paths_agree_on_uniform_and_mixed_masses(fold):
+    """mass_fold sums equal-mass j-tiles without the mass (12 FP64 ops per pair)
+    and scales once per tile; both paths must meet the same bar, on an
+    equal-mass system, on random masses and on a mixture of the two."""
+    n = 9000
+    m, x, y, vx, vy = g.plummer(n, seed=12)
+    rng = np.random.default_rng(5)
+    mixed = m.copy()
+    mixed[4000:] *= rng.uniform(0.1, 10.0, n - 4000)       # tiles 0..14 uniform, 15 mixed, rest random
+    mixed[123] = 0.0                                        # a massless tracer inside a uniform tile
+    for masses in (m, mixed):
+        with g.GravityCuda(n, kernel=g.KERNEL_TILED, mass_fold=fold) as h:
+            h.upload(masses, x, y, vx, vy)
+            ax, ay = h.accel(4)
+            h.step(4, 2)
+            got = h.download()
+        rax, ray = oracle.accel(masses, x, y, vx, vy, 4, nthreads=NTHREADS)
+        assert_accel_parity(ax, ay, rax, ray, (masses, x, y, vx, vy), 4)
+        want = oracle.step(masses, x, y, vx, vy, 4, 2, nthreads=NTHREADS)
+        for a, b in zip(got, want):
+            assert np.allclose(a, b, rtol=1e-11, atol=0)
+
+
 def test_tiled_accel_config3_full_65536():
     """BASELINE.json configs[2]: N = 65,536 on one GPU, accelerations against the
     oracle on the full set (4.3e9 pairs on the host)."""
@@ -264,7 +288,7 @@ def test_full_size_1m_properties_and_row_sample():
         pure = rel_err_rows(ax[rows], ay[rows], rax, ray)
         floor = 0.1 * np.median(np.hypot(rax, ray))
         assert (np.hypot(ax[rows] - rax, ay[rows] - ray) / np.maximum(np.hypot(rax, ray), floor)).max() <= ACCEL_TOL
-        assert (pure > ACCEL_TOL).sum() <= 1 and np.median(pure) <= 2e-14
+        assert (pure > ACCEL_TOL).sum() <= 1 and np.median(pure) <= 1e-13   # the reference sum itself carries ~sqrt(N) eps
         # one step moves every body by V*DT + A*DT^2/2 (sim_gravity.c:1213-1219)
         h.step(1, 1)
         nx, ny, nvx, nvy = h.download()
