@@ -710,10 +710,16 @@ int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
         // the whole batch in one single-CTA launch
         DeviceCtx &c = h->ctx[0];
         CUDA_TRY(h, cudaSetDevice(c.device));
-        const int threads = (int)(((h->n + 31) / 32) * 32);
         hot_event(h, c);
-        k_small_strict_steps<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
-                                                          (long long)nsteps);
+        if (h->n <= kPairMax) {
+            const int threads = (int)(((h->n * h->n + 31) / 32) * 32);
+            k_small_strict_steps_pairs<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
+                                                                    (long long)nsteps);
+        } else {
+            const int threads = (int)(((h->n + 31) / 32) * 32);
+            k_small_strict_steps<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
+                                                              (long long)nsteps);
+        }
         hot_event(h, c);
         h->launches++;
         h->hot_launches++;

@@ -524,6 +524,74 @@ __global__ void __launch_bounds__(kSmallMax) k_small_strict_steps(double2 *pos, 
     }
 }
 
+// N <= 32: one thread per ORDERED PAIR.  The pair terms tmp*XDIST, tmp*YDIST
+// (sim_gravity.c:1202-1204) are independent of one another, so all N*(N-1) of
+// them -- each a dependent sqrt -> multiply -> divide chain, the latency that
+// dominates tiny systems -- are evaluated at once; thread (i,0) then adds its row
+// in ascending j exactly as the reference does, so the bits are unchanged while a
+// step costs one pair latency plus N additions instead of N pair latencies.
+constexpr int kPairMax = 32;
+
+__global__ void __launch_bounds__(kPairMax * kPairMax) k_small_strict_steps_pairs(double2 *pos, double2 *vel,
+                                                                                const double *mass, int n,
+                                                                                double dt, long long nsteps)
+{
+    __shared__ double2 s_pos[kPairMax];
+    __shared__ double2 s_drift[kPairMax];
+    __shared__ double  s_mass[kPairMax];
+    __shared__ double2 s_term[kPairMax][kPairMax + 1];
+    __shared__ unsigned s_skip[kPairMax];          // bit j of s_skip[i]: pair (i,j) is skipped
+
+    const int  i      = threadIdx.x / n;
+    const int  j      = threadIdx.x - i * n;
+    const bool owner  = j == 0;                    // thread (i,0) owns body i
+    const bool active = i < n;
+    double2 p = make_double2(0.0, 0.0), v = make_double2(0.0, 0.0);
+    if (active && owner) {
+        p         = pos[i];
+        v         = vel[i];
+        s_mass[i] = mass[i];
+    }
+    for (long long s = 0; s < nsteps; ++s) {
+        if (active && owner) {
+            s_pos[i]   = p;
+            s_drift[i] = make_double2(half_drift(p.x, v.x, dt), half_drift(p.y, v.y, dt));
+            s_skip[i]  = 0u;
+        }
+        __syncthreads();
+        if (active) {
+            const double dx = __dsub_rn(s_pos[j].x, s_drift[i].x);
+            const double dy = __dsub_rn(s_pos[j].y, s_drift[i].y);
+            const double r  = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            if (j == i || r == 0.0) {              // sim_gravity.c:1191, :1199-1201
+                atomicOr(&s_skip[i], 1u << j);
+            } else {
+                const double t = __ddiv_rn(s_mass[j], __dmul_rn(__dmul_rn(r, r), r));
+                s_term[i][j]   = make_double2(__dmul_rn(t, dx), __dmul_rn(t, dy));
+            }
+        }
+        __syncthreads();
+        if (active && owner) {
+            const unsigned skip = s_skip[i];
+            double sx = 0.0, sy = 0.0;
+            for (int k = 0; k < n; ++k) {
+                if (skip & (1u << k)) continue;
+                sx = __dadd_rn(sx, s_term[i][k].x);
+                sy = __dadd_rn(sy, s_term[i][k].y);
+            }
+            double ax, ay;
+            kick_drift(sx, dt, p.x, v.x, p.x, v.x, ax);
+            kick_drift(sy, dt, p.y, v.y, p.y, v.y, ay);
+        }
+        // no third barrier: until the next one only owners touch shared memory,
+        // each its own row, and only after it has finished reading it
+    }
+    if (active && owner) {
+        pos[i] = p;
+        vel[i] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K4: energy diagnostic (per-body terms; the host adds them up)
 // ---------------------------------------------------------------------------
