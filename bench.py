@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: same as --steps")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", type=int, default=1)
+    ap.add_argument("--overlap", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--bodies-per-thread", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)

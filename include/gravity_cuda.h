@@ -144,6 +144,10 @@ int gravity_cuda_launch_count(const gravity_cuda_t *h, int64_t *launches);
  * launches that was.  Valid after timer_stop. */
 int gravity_cuda_kernel_time(gravity_cuda_t *h, double *ms_total, int64_t *launches);
 
+/* The individual launch durations behind gravity_cuda_kernel_time (ms, in launch
+ * order, at most `cap` of them); *count receives how many were recorded. */
+int gravity_cuda_kernel_times(gravity_cuda_t *h, double *ms_out, int64_t cap, int64_t *count);
+
 /* Dependent-free DFMA microbenchmark on `device`: measured FP64 FMA-pipe
  * throughput in TFLOP/s (2 flops per lane-FMA) and the SM clock it ran at
  * (MHz, from the device's clock64 against the event time). */

@@ -920,6 +920,24 @@ int gravity_cuda_kernel_time(gravity_cuda_t *h, double *ms_total, int64_t *launc
     return 0;
 }
 
+int gravity_cuda_kernel_times(gravity_cuda_t *h, double *ms_out, int64_t cap, int64_t *count)
+{
+    if (!h) return fail(nullptr, "kernel_times: NULL handle");
+    DeviceCtx &c = h->ctx[0];
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+    int64_t k = 0;
+    for (size_t e = 0; e + 1 < c.kev_used; e += 2, ++k) {
+        if (ms_out && k < cap) {
+            float t = 0.f;
+            CUDA_TRY(h, cudaEventElapsedTime(&t, c.kev[e], c.kev[e + 1]));
+            ms_out[k] = t;
+        }
+    }
+    if (count) *count = k;
+    return 0;
+}
+
 int gravity_cuda_launch_count(const gravity_cuda_t *h, int64_t *launches)
 {
     if (!h || !launches) return -1;

@@ -57,6 +57,7 @@ def load_cuda_library():
         "gravity_cuda_timer_stop": (C.c_int, [H, _dp]),
         "gravity_cuda_launch_count": (C.c_int, [H, C.POINTER(C.c_int64)]),
         "gravity_cuda_kernel_time": (C.c_int, [H, _dp, C.POINTER(C.c_int64)]),
+        "gravity_cuda_kernel_times": (C.c_int, [H, _dp, C.c_int64, C.POINTER(C.c_int64)]),
         "gravity_cuda_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
     }
     for name, (res, args) in sigs.items():
@@ -208,6 +209,12 @@ class GravityCuda:
         v = C.c_int64()
         self._check(self._lib.gravity_cuda_launch_count(self._h, C.byref(v)))
         return v.value
+
+    def kernel_times(self, cap=4096):
+        out = np.zeros(cap, dtype=np.float64)
+        cnt = C.c_int64()
+        self._check(self._lib.gravity_cuda_kernel_times(self._h, _ptr(out), cap, C.byref(cnt)))
+        return out[:min(cap, cnt.value)]
 
     def kernel_time(self):
         ms, cnt = C.c_double(), C.c_int64()

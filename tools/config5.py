@@ -21,7 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--bodies", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--rows", type=int, default=1024)
-ap.add_argument("--overlap", type=int, default=1)
+ap.add_argument("--overlap", type=int, default=0)
 ap.add_argument("--mass-fold", type=int, default=0)
 args = ap.parse_args()
 
