@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--bodies-per-thread", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--exchange", type=int, default=1,
+                    help="multi-GPU position exchange: 0 = NCCL all-gather, 1 = peer-memory stores from the commit kernel")
     ap.add_argument("--mass-fold", type=int, default=0,
                     help="headline kernel path: 0 = general masses (13 FP64 instr/pair, default), 1 = let equal-mass "
                          "j-tiles take the 12-instruction path")
@@ -217,6 +219,19 @@ def run_ours(args, rank, world, local_rank):
     if args.ctas_per_sm:
         opts["ctas_per_sm"] = args.ctas_per_sm
     h = g.GravityCuda(n, rank=rank, nranks=world, device=local_rank, nccl_id=nccl_id, **opts)
+    exchange = 0
+    if world > 1 and args.exchange == 1:
+        # peer-memory exchange; if the peers cannot be mapped every rank stays on
+        # the NCCL all-gather (still GPU-to-GPU over NVLink; recorded in config)
+        try:
+            h.p2p_connect(ranks.all_gather_bytes(h.p2p_export()))
+            ok = 1.0
+        except g.GravityError as e:
+            sys.stderr.write("rank %d: peer-memory exchange unavailable (%s)\n" % (rank, e))
+            ok = 0.0
+        if ranks.sum(ok) == world:
+            h.set_option("exchange", 1)
+            exchange = 1
 
     fp64_tf, fp64_mhz = g.fp64_peak(local_rank) if rank == 0 else (None, None)
 
@@ -313,12 +328,14 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "planar Plummer model N=%d, DT=1 s, seed 1 (BASELINE.json configs[4] size)" % n,
-                       "bodies": n, "parallelism": "i-sharded x%d, NCCL all-gather of positions per step" % world,
+                       "bodies": n, "parallelism": "i-sharded x%d, %s" % (world, "peer-memory stores of the new positions from the commit "
+                                       "kernel + step flags" if exchange == 1 else
+                                       "NCCL all-gather of positions per step"),
                        "l2": "compute-bound: 24*N bytes of j-state stream from L2/HBM per i-block, no flush needed; "
                              "inputs change every step",
                        "kernel": "tiled rsqrt, general masses, 13 FP64-pipe instr/pair" if not args.mass_fold else
                                  "tiled rsqrt, equal-mass tiles folded, 12 FP64-pipe instr/pair",
-                       "overlap": args.overlap, "mass_fold": args.mass_fold},
+                       "overlap": args.overlap, "mass_fold": args.mass_fold, "exchange": exchange},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 5 * 8 * n * world,
                     "d2h_bytes_per_step": 4 * 8 * n * world, "steps": e2e_steps, "checksum_x": checksum},

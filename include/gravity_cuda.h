@@ -56,6 +56,7 @@ typedef struct gravity_cuda gravity_cuda_t;
                                              bit-identical to sim_gravity.c      */
 
 #define GRAVITY_CUDA_NCCL_ID_BYTES 128
+#define GRAVITY_CUDA_P2P_BLOB_BYTES 256
 
 /* ---- life cycle --------------------------------------------------------- */
 
@@ -73,6 +74,17 @@ int gravity_cuda_nccl_unique_id(void *id_out, size_t id_bytes);
 int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nranks,
                              int device, const void *nccl_id, size_t id_bytes);
 
+/* Peer-memory exchange (option "exchange" = 1).  Instead of an NCCL all-gather,
+ * the commit kernel stores each new position straight into every peer's copy
+ * of the next position buffer over NVLink and publishes a step flag; the next
+ * step's pair kernel waits for the flags.  Barrier B2 and the commit copy of the
+ * reference (sim_gravity.c:1226, :1242-1245) thus cost no separate launch.
+ * A single-process handle connects itself when the option is set.  Rank-mode
+ * handles exchange one GRAVITY_CUDA_P2P_BLOB_BYTES blob per rank through the
+ * host: export on every rank, all-gather the blobs in rank order, connect. */
+int gravity_cuda_p2p_export(gravity_cuda_t *h, void *blob, size_t bytes);
+int gravity_cuda_p2p_connect(gravity_cuda_t *h, const void *blobs_all_ranks, size_t bytes);
+
 /* Replaces sim_gravity_terminate's worker join (sim_gravity.c:487-502). */
 void gravity_cuda_destroy(gravity_cuda_t *h);
 
@@ -83,6 +95,8 @@ const char *gravity_cuda_last_error(const gravity_cuda_t *h);
 /* Options: "kernel" (GRAVITY_CUDA_KERNEL_*), "threads" (CTA size of the tiled
  * kernel: 128|256), "bodies_per_thread" (1|2|4), "ctas_per_sm" (1..8),
  * "overlap" (0|1: start the local j-shard while the all-gather is in flight),
+ * "exchange" (0: NCCL all-gather of the new positions, default; 1: peer-memory
+ * stores + flags, see gravity_cuda_p2p_connect),
  * "mass_fold" (0|1, default 1: j-tiles whose 256 masses are bit-identical are
  * summed without the mass and scaled once per tile -- 12 instead of 13 FP64
  * instructions per pair; results differ from mass_fold=0 by rounding only).

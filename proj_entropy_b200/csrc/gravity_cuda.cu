@@ -38,6 +38,15 @@ struct DeviceCtx {
     double2 *vel = nullptr;
     double2 *accel = nullptr;
     double  *tile_mass = nullptr;  // [npad / kTile], see k_tile_mass
+    double2 *gather_tmp = nullptr; // [npad] scratch for gathering velocities / accelerations
+
+    // peer-memory exchange
+    unsigned long long *flags = nullptr;           // [kMaxPeers], written by the peers
+    unsigned int       *commit_counter = nullptr;
+    unsigned int       *status = nullptr;
+    double2            *peer_pos[2][kMaxPeers] = {};
+    unsigned long long *peer_flags[kMaxPeers] = {};
+    bool                ipc_opened[kMaxPeers] = {};
     double  *stage = nullptr;      // 4 x npad doubles: SoA staging for upload / download
     double  *kin = nullptr, *pot = nullptr;
     double2 *partial = nullptr;
@@ -73,6 +82,9 @@ struct gravity_cuda {
     bool uploaded = false, planned = false;
     int opt_kernel = GRAVITY_CUDA_KERNEL_AUTO;
     int opt_threads = 256, opt_bpt = 4, opt_ctas_per_sm = 1, opt_overlap = 0, opt_mass_fold = 1;
+    int opt_exchange = 0;            // 0: NCCL all-gather, 1: peer-memory stores + flags
+    bool p2p_connected = false;
+    unsigned long long step_id = 0;  // commits published so far (peer-memory exchange)
     int64_t launches = 0;
     bool timing = false;
     int64_t hot_launches = 0;
@@ -304,6 +316,13 @@ int launch_tiled_phase(gravity_cuda_t *h, DeviceCtx &c, int phase, double dt)
     P.i_global0 = c.i0;
     P.n_local = c.n_local;
     P.dt = dt;
+    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
+    P.wait_flags = p2p ? c.flags : nullptr;
+    P.wait_status = c.status;
+    P.wait_step = h->step_id;
+    P.wait_rank = c.rank;
+    P.wait_nranks = h->nranks;
+    if (c.n_phase == 2 && phase == 0) P.wait_flags = nullptr;   // local j-tiles need no peer data
     accum_kernel_t k = pick_accum(c.threads, c.bpt, c.minb);
     hot_event(h, c);
     k<<<ph.n_cta, c.threads, 0, c.stream>>>(P);
@@ -330,6 +349,21 @@ CommitParams commit_params(gravity_cuda_t *h, DeviceCtx &c, double dt, bool expo
     P.iblock_size = c.threads * c.bpt;
     P.export_accel = export_accel ? 1 : 0;
     P.dt = dt;
+    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
+    P.wait_flags = p2p ? c.flags : nullptr;
+    P.wait_step = h->step_id;
+    memset(&P.px, 0, sizeof(P.px));
+    P.px.enabled = (p2p && !export_accel) ? 1 : 0;
+    P.px.rank = c.rank;
+    P.px.nranks = h->nranks;
+    P.px.flags = c.flags;
+    P.px.commit_counter = c.commit_counter;
+    P.px.status = c.status;
+    P.px.step = h->step_id + 1;
+    for (int r = 0; r < h->nranks && r < kMaxPeers; ++r) {
+        P.px.peer_next[r] = c.peer_pos[h->cur ^ 1][r];
+        P.px.peer_flags[r] = c.peer_flags[r];
+    }
     return P;
 }
 
@@ -343,7 +377,16 @@ int enqueue_evaluation(gravity_cuda_t *h, double dt, bool export_accel, bool gat
     }
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
-        if (c.n_local == 0) continue;
+        if (c.n_local == 0) {
+            // an empty shard still has to tell its peers that it has nothing to send
+            if (h->opt_exchange == 1 && h->nranks > 1 && !export_accel) {
+                const CommitParams P = commit_params(h, c, dt, false);
+                k_commit_partials<<<1, kCommitThreads, 0, c.stream>>>(P);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+            }
+            continue;
+        }
         if (kernel == GRAVITY_CUDA_KERNEL_TILED) {
             if (launch_tiled_phase(h, c, 0, dt) != 0) return -1;
             if (c.n_phase == 2) {
@@ -366,7 +409,9 @@ int enqueue_evaluation(gravity_cuda_t *h, double dt, bool export_accel, bool gat
         }
         CUDA_TRY(h, cudaGetLastError());
     }
-    if (!export_accel && gather_after && h->nranks > 1) {
+    if (!export_accel && gather_after && h->nranks > 1 && h->opt_exchange == 1) {
+        h->step_id++;      // the commit kernels stored into the peers and will publish this step
+    } else if (!export_accel && gather_after && h->nranks > 1) {
         // barrier B2 + the NEXT_* -> state copy (sim_gravity.c:1226, :1242-1245)
         // become one in-place all-gather of the new positions.
         const bool two_stream = h->opt_overlap != 0;
@@ -395,6 +440,29 @@ int enqueue_evaluation(gravity_cuda_t *h, double dt, bool export_accel, bool gat
     return 0;
 }
 
+// peer-memory exchange: make the stream wait until every peer's positions of
+// the current step have landed in this device's pos[cur]
+int enqueue_wait_peers(gravity_cuda_t *h, DeviceCtx &c)
+{
+    if (!(h->opt_exchange == 1 && h->nranks > 1)) return 0;
+    k_wait_peers<<<1, 32, 0, c.stream>>>(c.flags, h->step_id, c.rank, h->nranks, c.status);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int check_exchange_status(gravity_cuda_t *h)
+{
+    if (!(h->opt_exchange == 1 && h->nranks > 1)) return 0;
+    for (DeviceCtx &c : h->ctx) {
+        unsigned int st = 0;
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaMemcpy(&st, c.status, sizeof(st), cudaMemcpyDeviceToHost));
+        if (st != 0) return fail(h, "peer-memory exchange timed out on rank %d: a peer never published its step", c.rank);
+    }
+    return 0;
+}
+
 int sync_all(gravity_cuda_t *h)
 {
     for (DeviceCtx &c : h->ctx) {
@@ -402,6 +470,19 @@ int sync_all(gravity_cuda_t *h)
         CUDA_TRY(h, cudaStreamSynchronize(c.stream));
         CUDA_TRY(h, cudaStreamSynchronize(c.comm_stream));
     }
+    return 0;
+}
+
+// every rank has finished everything it enqueued (used where a rank is about to
+// overwrite state that a peer may still be storing into)
+int rank_barrier(gravity_cuda_t *h)
+{
+    if (sync_all(h) != 0) return -1;
+    if (h->single_process || h->nranks == 1) return 0;      // one host thread drives every device
+    DeviceCtx &c = h->ctx[0];
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    NCCL_TRY(h, ncclAllReduce(c.kin, c.kin, 1, ncclDouble, ncclSum, c.comm, c.stream));
+    CUDA_TRY(h, cudaStreamSynchronize(c.stream));
     return 0;
 }
 
@@ -436,6 +517,13 @@ int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
     CUDA_TRY(h, cudaMalloc(&c.accel, sizeof(double2) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.stage, sizeof(double) * 4 * h->npad));
     CUDA_TRY(h, cudaMalloc(&c.tile_mass, sizeof(double) * (h->npad / kTile)));
+    CUDA_TRY(h, cudaMalloc(&c.gather_tmp, sizeof(double2) * h->npad));
+    CUDA_TRY(h, cudaMalloc(&c.flags, sizeof(unsigned long long) * kMaxPeers));
+    CUDA_TRY(h, cudaMalloc(&c.commit_counter, sizeof(unsigned int)));
+    CUDA_TRY(h, cudaMalloc(&c.status, sizeof(unsigned int)));
+    CUDA_TRY(h, cudaMemsetAsync(c.flags, 0, sizeof(unsigned long long) * kMaxPeers, c.stream));
+    CUDA_TRY(h, cudaMemsetAsync(c.commit_counter, 0, sizeof(unsigned int), c.stream));
+    CUDA_TRY(h, cudaMemsetAsync(c.status, 0, sizeof(unsigned int), c.stream));
     CUDA_TRY(h, cudaMalloc(&c.kin, sizeof(double) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.pot, sizeof(double) * h->chunk));
     CUDA_TRY(h, cudaMemsetAsync(c.vel, 0, sizeof(double2) * h->chunk, c.stream));
@@ -576,7 +664,15 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
         if (c.comm_stream) cudaStreamSynchronize(c.comm_stream);
         if (c.comm) ncclCommDestroy(c.comm);
         cudaFree(c.pos[0]); cudaFree(c.pos[1]); cudaFree(c.mass); cudaFree(c.vel); cudaFree(c.accel);
-        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.tile_mass); cudaFree(c.partial); cudaFree(c.seg);
+        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.tile_mass);
+        for (int r = 0; r < kMaxPeers; ++r) {
+            if (c.ipc_opened[r]) {
+                cudaIpcCloseMemHandle(c.peer_pos[0][r]);
+                cudaIpcCloseMemHandle(c.peer_pos[1][r]);
+                cudaIpcCloseMemHandle(c.peer_flags[r]);
+            }
+        }
+        cudaFree(c.gather_tmp); cudaFree(c.flags); cudaFree(c.commit_counter); cudaFree(c.status); cudaFree(c.partial); cudaFree(c.seg);
         cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin);
         for (cudaEvent_t e : c.kev) cudaEventDestroy(e);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
@@ -587,6 +683,84 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
         if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
     }
     delete h;
+}
+
+namespace {
+struct P2PBlob {
+    cudaIpcMemHandle_t pos[2];
+    cudaIpcMemHandle_t flags;
+    int rank;
+};
+static_assert(sizeof(P2PBlob) <= GRAVITY_CUDA_P2P_BLOB_BYTES, "blob too large");
+}  // namespace
+
+int gravity_cuda_p2p_export(gravity_cuda_t *h, void *blob, size_t bytes)
+{
+    if (!h || !blob) return fail(h, "p2p_export: NULL argument");
+    if (bytes < GRAVITY_CUDA_P2P_BLOB_BYTES) return fail(h, "p2p_export: blob buffer too small");
+    if (h->single_process) return fail(h, "p2p_export is for rank-mode handles; a single-process handle connects itself");
+    DeviceCtx &c = h->ctx[0];
+    P2PBlob b;
+    memset(&b, 0, sizeof(b));
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.pos[0], c.pos[0]));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.pos[1], c.pos[1]));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.flags, c.flags));
+    b.rank = c.rank;
+    memset(blob, 0, bytes);
+    memcpy(blob, &b, sizeof(b));
+    return 0;
+}
+
+int gravity_cuda_p2p_connect(gravity_cuda_t *h, const void *blobs, size_t bytes)
+{
+    if (!h) return fail(nullptr, "p2p_connect: NULL handle");
+    if (h->nranks > kMaxPeers) return fail(h, "peer-memory exchange supports at most %d ranks", kMaxPeers);
+    if (h->p2p_connected) return 0;
+    if (h->single_process) {
+        for (DeviceCtx &a : h->ctx) {
+            CUDA_TRY(h, cudaSetDevice(a.device));
+            for (DeviceCtx &b : h->ctx) {
+                if (&a != &b) {
+                    int can = 0;
+                    CUDA_TRY(h, cudaDeviceCanAccessPeer(&can, a.device, b.device));
+                    if (!can) return fail(h, "device %d cannot access device %d's memory", a.device, b.device);
+                    cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e != cudaSuccess) return fail(h, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+                }
+                a.peer_pos[0][b.rank] = b.pos[0];
+                a.peer_pos[1][b.rank] = b.pos[1];
+                a.peer_flags[b.rank] = b.flags;
+            }
+        }
+    } else {
+        if (!blobs || bytes < (size_t)h->nranks * GRAVITY_CUDA_P2P_BLOB_BYTES)
+            return fail(h, "p2p_connect: need %d blobs of %d bytes", h->nranks, GRAVITY_CUDA_P2P_BLOB_BYTES);
+        DeviceCtx &c = h->ctx[0];
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        for (int r = 0; r < h->nranks; ++r) {
+            if (r == c.rank) {
+                c.peer_pos[0][r] = c.pos[0];
+                c.peer_pos[1][r] = c.pos[1];
+                c.peer_flags[r] = c.flags;
+                continue;
+            }
+            P2PBlob b;
+            memcpy(&b, static_cast<const char *>(blobs) + (size_t)r * GRAVITY_CUDA_P2P_BLOB_BYTES, sizeof(b));
+            if (b.rank != r) return fail(h, "p2p_connect: blob %d belongs to rank %d", r, b.rank);
+            void *p0 = nullptr, *p1 = nullptr, *pf = nullptr;
+            CUDA_TRY(h, cudaIpcOpenMemHandle(&p0, b.pos[0], cudaIpcMemLazyEnablePeerAccess));
+            CUDA_TRY(h, cudaIpcOpenMemHandle(&p1, b.pos[1], cudaIpcMemLazyEnablePeerAccess));
+            CUDA_TRY(h, cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess));
+            c.peer_pos[0][r] = static_cast<double2 *>(p0);
+            c.peer_pos[1][r] = static_cast<double2 *>(p1);
+            c.peer_flags[r] = static_cast<unsigned long long *>(pf);
+            c.ipc_opened[r] = true;
+        }
+    }
+    h->p2p_connected = true;
+    return 0;
 }
 
 int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
@@ -608,6 +782,15 @@ int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
         h->opt_overlap = value ? 1 : 0;
     } else if (!strcmp(key, "mass_fold")) {
         h->opt_mass_fold = value ? 1 : 0;
+    } else if (!strcmp(key, "exchange")) {
+        if (value != 0 && value != 1) return fail(h, "exchange must be 0 (NCCL all-gather) or 1 (peer memory)");
+        if (value == 1 && h->nranks > 1 && !h->p2p_connected) {
+            if (!h->single_process)
+                return fail(h, "exchange=1 in rank mode needs gravity_cuda_p2p_connect() first");
+            if (gravity_cuda_p2p_connect(h, nullptr, 0) != 0) return -1;
+        }
+        if (rank_barrier(h) != 0) return -1;
+        h->opt_exchange = (int)value;
     } else {
         return fail(h, "unknown option '%s'", key);
     }
@@ -620,7 +803,7 @@ int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, 
 {
     if (!h) return fail(nullptr, "upload: NULL handle");
     if (!mass || !x || !y || !vx || !vy) return fail(h, "upload: NULL array");
-    if (sync_all(h) != 0) return -1;
+    if (rank_barrier(h) != 0) return -1;
     const int64_t n = h->n, np = h->npad;
     h->cur = 0;
     for (DeviceCtx &c : h->ctx) {
@@ -657,6 +840,7 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
         DeviceCtx &c = h->ctx[0];
         CUDA_TRY(h, cudaSetDevice(c.device));
         double *sx = c.stage, *sy = c.stage + np;
+        if (enqueue_wait_peers(h, c) != 0) return -1;
         k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(c.pos[h->cur], sx, sy, n);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
@@ -679,23 +863,19 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
             // rank mode: gather the velocity shards through the spare position buffer
             DeviceCtx &c = h->ctx[0];
             CUDA_TRY(h, cudaSetDevice(c.device));
-            double2 *tmp = c.pos[h->cur ^ 1];
+            double2 *tmp = c.gather_tmp;
             double *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
             CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.vel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
             NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
             k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(tmp, svx, svy, n);
             h->launches++;
-            // restore the padding the gather overwrote with velocity padding (zeros)
-            const int64_t npadding = h->npad - h->n;
-            if (npadding > 0) {
-                k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(tmp, tmp, c.mass, h->n, h->npad);
-            }
             CUDA_TRY(h, cudaGetLastError());
             if (vx) CUDA_TRY(h, cudaMemcpyAsync(vx, svx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
             if (vy) CUDA_TRY(h, cudaMemcpyAsync(vy, svy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
         }
     }
-    return sync_all(h);
+    if (sync_all(h) != 0) return -1;
+    return check_exchange_status(h);
 }
 
 int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
@@ -736,7 +916,8 @@ int gravity_cuda_sync(gravity_cuda_t *h)
 {
     if (!h) return fail(nullptr, "sync: NULL handle");
     if (join_comm(h) != 0) return -1;
-    return sync_all(h);
+    if (sync_all(h) != 0) return -1;
+    return check_exchange_status(h);
 }
 
 int gravity_cuda_step(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
@@ -768,16 +949,12 @@ int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay)
     } else {
         DeviceCtx &c = h->ctx[0];
         CUDA_TRY(h, cudaSetDevice(c.device));
-        double2 *tmp = c.pos[h->cur ^ 1];
+        double2 *tmp = c.gather_tmp;
         double *sx = c.stage, *sy = c.stage + np;
         CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.accel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
         NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
         k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(tmp, sx, sy, n);
         h->launches++;
-        const int64_t npadding = h->npad - h->n;
-        if (npadding > 0) {
-            k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(tmp, tmp, c.mass, h->n, h->npad);
-        }
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaMemcpyAsync(ax, sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
         CUDA_TRY(h, cudaMemcpyAsync(ay, sy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
@@ -836,6 +1013,7 @@ int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential)
         P.i_global0 = c.i0;
         P.n_local = c.n_local;
         const int grid = (int)((c.n_local + kEnergyThreads - 1) / kEnergyThreads);
+        if (enqueue_wait_peers(h, c) != 0) return -1;
         k_energy_terms<<<grid, kEnergyThreads, 0, c.stream>>>(P);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());

@@ -24,6 +24,25 @@ constexpr int    kLookahead   = 2;       // tiles in flight ahead of the consume
 constexpr int    kSmallMax    = 1024;    // largest N of the single-CTA kernel
 constexpr double kG           = 6.673E-11;   // sim_gravity.c:29
 constexpr double kPadCoord    = 1.0e150;     // parking spot of padding bodies
+constexpr int    kMaxPeers    = 16;          // ranks of the peer-memory exchange
+constexpr long long kSpinTimeoutCycles = 20000000000LL;   // ~10 s: give up instead of hanging
+
+// Peer-memory exchange (replaces the NCCL all-gather when connected): the commit
+// kernel stores every new position into each peer's copy of pos_next over
+// NVLink and, when its last CTA is done, publishes its step number in each
+// peer's flag array; the next step's pair kernel waits until every peer's flag
+// has reached the step it is about to read.
+struct PeerExchange {
+    double2            *peer_next[kMaxPeers];    // pos_next of every rank, as mapped here
+    unsigned long long *peer_flags[kMaxPeers];   // flag array of every rank, as mapped here
+    unsigned long long *flags;                   // this rank's own flag array [kMaxPeers]
+    unsigned int       *commit_counter;          // last-CTA detection
+    unsigned int       *status;                  // != 0: a wait timed out
+    unsigned long long  step;                    // commit: value to publish; wait: value required
+    int32_t             rank, nranks;
+    int32_t             enabled;
+    int32_t             reserved;
+};
 
 // One contiguous run of j-tiles for one block of i-bodies, executed by one CTA.
 struct Segment {
@@ -45,6 +64,10 @@ struct AccumParams {
     int64_t        i_global0;       // global index of local body 0
     int64_t        n_local;         // real bodies in the local shard
     double         dt;              // (double)DT
+    const unsigned long long *wait_flags;   // NULL, or this rank's flag array
+    unsigned int  *wait_status;
+    unsigned long long wait_step;
+    int32_t        wait_rank, wait_nranks;
 };
 
 struct CommitParams {
@@ -61,6 +84,9 @@ struct CommitParams {
     int32_t        iblock_size;     // IB of the accumulate kernel
     int32_t        export_accel;    // 1: write AX,AY and leave the state alone
     double         dt;
+    const unsigned long long *wait_flags;   // strict kernel only: it reads pos_cur itself
+    unsigned long long wait_step;
+    PeerExchange   px;
 };
 
 // ---------------------------------------------------------------------------
@@ -111,6 +137,66 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Peer-memory exchange helpers
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by every thread of a CTA before it reads time-t positions: lanes
+// 0..nranks-1 of warp 0 each wait for one peer's flag.  A peer that never arrives
+// is reported through *status after ~10 s instead of hanging the GPU.
+__device__ __forceinline__ void wait_for_peers(const unsigned long long *flags, unsigned long long step,
+                                               int rank, int nranks, unsigned int *status)
+{
+    if (flags != nullptr) {
+        const int t = threadIdx.x;
+        if (t < nranks && t != rank) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(flags + t) < step) {
+                if (clock64() - t0 > kSpinTimeoutCycles) {
+                    if (status) atomicExch(status, 1u);
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        // the tiles are fetched by the async proxy (bulk copies)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
+}
+
+// Called by every thread of the commit grid after its stores: when the last CTA
+// gets here all new positions of this rank are visible system-wide and the step
+// number is published to every peer.
+__device__ __forceinline__ void publish_to_peers(const PeerExchange &X)
+{
+    if (!X.enabled) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(X.commit_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *X.commit_counter = 0u;                      // ready for the next launch
+            __threadfence_system();
+            for (int r = 0; r < X.nranks; ++r) {
+                if (r != X.rank) st_release_sys(X.peer_flags[r] + X.rank, X.step);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -257,6 +343,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
         mbar_fence_init();
     }
     __syncthreads();
+    wait_for_peers(P.wait_flags, P.wait_step, P.wait_rank, P.wait_nranks, P.wait_status);
 
     // producer cursor (meaningful in thread 0 only)
     int p_seg = seg_begin, p_tile = 0, p_tile_end = 0, issued = 0;
@@ -390,8 +477,16 @@ __device__ __forceinline__ void commit_body(const CommitParams &P, int64_t li, d
     if (P.export_accel) {
         P.accel_out[li] = make_double2(ax, ay);          // sim_gravity.c:1207-1208
     } else {
-        P.pos_next[gi] = make_double2(nx, ny);           // NEXT_X, NEXT_Y  (:1218-1219)
+        const double2 pn = make_double2(nx, ny);
+        P.pos_next[gi] = pn;                             // NEXT_X, NEXT_Y  (:1218-1219)
         P.vel[li]      = make_double2(nvx, nvy);         // NEXT_VX, NEXT_VY (:1220-1221)
+        if (P.px.enabled) {
+            // barrier B2 + the commit copy (:1226, :1242-1245): every peer gets
+            // the new position straight into its own pos_next over NVLink
+            for (int r = 0; r < P.px.nranks; ++r) {
+                if (r != P.px.rank) P.px.peer_next[r][gi] = pn;
+            }
+        }
     }
 }
 
@@ -440,6 +535,7 @@ __global__ void __launch_bounds__(kCommitThreads) k_commit_partials(const Commit
         sy = s_fixed[threadIdx.x].y;
     }
     if (active) commit_body(P, li, sx, sy);
+    if (!P.export_accel) publish_to_peers(P.px);
 }
 
 // ---------------------------------------------------------------------------
@@ -458,6 +554,7 @@ __global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitPara
     const bool    active = li < P.n_local;
     const int64_t gi     = P.i_global0 + li;
     double px = 0.0, py = 0.0, sx = 0.0, sy = 0.0;
+    wait_for_peers(P.wait_flags, P.wait_step, P.px.rank, P.px.nranks, P.px.status);
     if (active) {
         const double2 p = P.pos_cur[gi];
         const double2 v = P.vel[li];
@@ -481,6 +578,14 @@ __global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitPara
         }
     }
     if (active) commit_body(P, li, sx, sy);
+    if (!P.export_accel) publish_to_peers(P.px);
+}
+
+// Stream-ordered wait for the peers' positions (download, energy): one warp.
+__global__ void k_wait_peers(const unsigned long long *flags, unsigned long long step, int rank, int nranks,
+                             unsigned int *status)
+{
+    wait_for_peers(flags, step, rank, nranks, status);
 }
 
 // N <= 1024, one device: the whole system lives in one CTA and `nsteps` steps

@@ -70,6 +70,17 @@ class Ranks:
         self.dist.broadcast(buf, src)
         return bytes(buf.cpu().numpy().tobytes())
 
+    def all_gather_bytes(self, payload):
+        """Every rank passes `payload` (same length everywhere); returns the
+        concatenation in rank order."""
+        if self.dist is None:
+            return bytes(payload)
+        import torch
+        mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(self.device)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine)
+        return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
+
     def close(self):
         if self.dist is not None:
             self.dist.barrier()

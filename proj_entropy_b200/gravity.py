@@ -13,6 +13,7 @@ import numpy as np
 
 KERNEL_AUTO, KERNEL_TILED, KERNEL_STRICT = 0, 1, 2
 NCCL_ID_BYTES = 128
+P2P_BLOB_BYTES = 256
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -42,6 +43,8 @@ def load_cuda_library():
         "gravity_cuda_create": (C.c_int, [C.POINTER(H), C.c_int64, C.c_int]),
         "gravity_cuda_create_rank": (C.c_int, [C.POINTER(H), C.c_int64, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p, C.c_size_t]),
+        "gravity_cuda_p2p_export": (C.c_int, [H, C.c_void_p, C.c_size_t]),
+        "gravity_cuda_p2p_connect": (C.c_int, [H, C.c_void_p, C.c_size_t]),
         "gravity_cuda_destroy": (None, [H]),
         "gravity_cuda_set_option": (C.c_int, [H, C.c_char_p, C.c_int64]),
         "gravity_cuda_upload": (C.c_int, [H, _dp, _dp, _dp, _dp, _dp]),
@@ -151,6 +154,20 @@ class GravityCuda:
     # -- the C ABI, one method per entry point --------------------------------
     def set_option(self, key, value):
         self._check(self._lib.gravity_cuda_set_option(self._h, key.encode(), int(value)))
+
+    def p2p_export(self):
+        buf = (C.c_ubyte * P2P_BLOB_BYTES)()
+        self._check(self._lib.gravity_cuda_p2p_export(self._h, buf, P2P_BLOB_BYTES))
+        return bytes(buf)
+
+    def p2p_connect(self, blobs=None):
+        """blobs: the P2P_BLOB_BYTES blobs of all ranks concatenated in rank order
+        (rank mode), or None for a single-process handle."""
+        if blobs is None:
+            self._check(self._lib.gravity_cuda_p2p_connect(self._h, None, 0))
+        else:
+            buf = (C.c_ubyte * len(blobs)).from_buffer_copy(blobs)
+            self._check(self._lib.gravity_cuda_p2p_connect(self._h, buf, len(blobs)))
 
     def upload(self, mass, x, y, vx, vy):
         n = self.n

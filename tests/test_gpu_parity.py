@@ -301,8 +301,10 @@ def test_full_size_1m_properties_and_row_sample():
 # ---------------------------------------------------------------------------
 
 @pytest.mark.multigpu
-@pytest.mark.parametrize("overlap", [0, 1])
-def test_two_gpus_agree_with_one(gpu_count, overlap):
+@pytest.mark.parametrize("overlap,exchange", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_two_gpus_agree_with_one(gpu_count, overlap, exchange):
+    """exchange=0: NCCL all-gather; exchange=1: the commit kernel stores into the
+    peer's position buffer over NVLink and publishes a step flag."""
     if gpu_count < 2:
         pytest.skip("needs 2 GPUs")
     n = 30000
@@ -311,10 +313,14 @@ def test_two_gpus_agree_with_one(gpu_count, overlap):
         h1.upload(m, x, y, vx, vy)
         h1.step(5, 4)
         one = h1.download()
-    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_TILED, overlap=overlap) as h2:
+    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_TILED, overlap=overlap, exchange=exchange) as h2:
         h2.upload(m, x, y, vx, vy)
-        h2.step(5, 4)
+        h2.step(5, 3)
+        h2.accel(5)                      # an evaluation that must not disturb the exchange
+        h2.step(5, 1)
+        ke, pe = h2.energy()
         two = h2.download()
+        assert np.isfinite(ke + pe)
     for a, b in zip(one, two):
         assert np.allclose(a, b, rtol=1e-12, atol=0)
     want = oracle.step(m, x, y, vx, vy, 5, 4, nthreads=NTHREADS)
@@ -323,12 +329,13 @@ def test_two_gpus_agree_with_one(gpu_count, overlap):
 
 
 @pytest.mark.multigpu
-def test_two_gpus_strict_is_still_bit_exact(gpu_count):
+@pytest.mark.parametrize("exchange", [0, 1])
+def test_two_gpus_strict_is_still_bit_exact(gpu_count, exchange):
     if gpu_count < 2:
         pytest.skip("needs 2 GPUs")
     n = 1500
     m, x, y, vx, vy = g.plummer(n, seed=8)
-    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_STRICT) as h:
+    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_STRICT, exchange=exchange) as h:
         h.upload(m, x, y, vx, vy)
         h.step(9, 3)
         got = h.download()
@@ -387,3 +394,20 @@ def test_upload_download_round_trip_bits():
         got = h.download()
     for a, b in zip(got, (x, y, vx, vy)):
         assert bits_equal(a, b)
+
+
+@pytest.mark.multigpu
+def test_peer_exchange_with_an_empty_shard(gpu_count):
+    """N smaller than one shard: the second GPU owns no body but still has to
+    publish its step flag, or the first would wait for ever."""
+    if gpu_count < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 200
+    m, x, y, vx, vy = g.plummer(n, seed=13)
+    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_TILED, exchange=1) as h:
+        h.upload(m, x, y, vx, vy)
+        h.step(3, 5)
+        got = h.download()
+    want = oracle.step(m, x, y, vx, vy, 3, 5)
+    for a, b in zip(got, want):
+        assert np.allclose(a, b, rtol=1e-11, atol=0)

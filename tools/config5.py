@@ -23,6 +23,7 @@ ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--rows", type=int, default=1024)
 ap.add_argument("--overlap", type=int, default=0)
 ap.add_argument("--mass-fold", type=int, default=0)
+ap.add_argument("--exchange", type=int, default=0)
 args = ap.parse_args()
 
 ranks = Ranks("nccl")
@@ -31,6 +32,9 @@ state = g.plummer(n, seed=1)
 nccl_id = ranks.broadcast_bytes(g.nccl_unique_id() if ranks.rank == 0 else None, 128) if ranks.world > 1 else None
 h = g.GravityCuda(n, rank=ranks.rank, nranks=ranks.world, device=ranks.local_rank, nccl_id=nccl_id,
                   kernel=g.KERNEL_TILED, overlap=args.overlap, mass_fold=args.mass_fold)
+if ranks.world > 1 and args.exchange == 1:
+    h.p2p_connect(ranks.all_gather_bytes(h.p2p_export()))
+    h.set_option("exchange", 1)
 h.upload(*state)
 rows = np.linspace(0, n - 1, args.rows).astype(np.int64)
 
@@ -81,7 +85,7 @@ if ranks.rank == 0:
         "hot_kernel_share_of_step_rank0": kms / ms if ms else None, "hot_kernel_launches_rank0": kl,
         "parity": [p0, p1],
         "energy": {"e0": ke0 + pe0, "e1": ke1 + pe1, "relative_drift": (ke1 + pe1 - ke0 - pe0) / abs(ke0 + pe0)},
-        "options": {"overlap": args.overlap, "mass_fold": args.mass_fold},
+        "options": {"overlap": args.overlap, "mass_fold": args.mass_fold, "exchange": args.exchange},
     }), flush=True)
 h.close()
 ranks.close()
