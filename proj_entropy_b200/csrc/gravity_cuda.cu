@@ -890,11 +890,31 @@ int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
         // the whole batch in one single-CTA launch
         DeviceCtx &c = h->ctx[0];
         CUDA_TRY(h, cudaSetDevice(c.device));
+        int coop = 0;
+        CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
         hot_event(h, c);
         if (h->n <= kPairMax) {
             const int threads = (int)(((h->n * h->n + 31) / 32) * 32);
             k_small_strict_steps_pairs<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
                                                                     (long long)nsteps);
+        } else if (coop) {
+            CoopParams P;
+            P.pos[0] = c.pos[0];
+            P.pos[1] = c.pos[1];
+            P.vel = c.vel;
+            P.mass = c.mass;
+            P.n = (int)h->n;
+            P.bodies_per_cta = (int)((h->n + c.num_sms - 1) / c.num_sms);
+            P.cur = h->cur;
+            P.dt = dtd;
+            P.nsteps = (long long)nsteps;
+            const int grid = (int)((h->n + P.bodies_per_cta - 1) / P.bodies_per_cta);
+            const size_t smem = coop_smem_bytes(P.n, P.bodies_per_cta);
+            CUDA_TRY(h, cudaFuncSetAttribute(k_strict_coop_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            void *args[] = {&P};
+            CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)k_strict_coop_steps, dim3(grid), dim3(kCoopThreads),
+                                                    args, smem, c.stream));
+            h->cur ^= (int)(nsteps & 1);      // the state ends in the other buffer after an odd number of steps
         } else {
             const int threads = (int)(((h->n + 31) / 32) * 32);
             k_small_strict_steps<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,

@@ -13,6 +13,7 @@
 // updated; they contribute exactly 0 to every sum.
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -695,6 +696,100 @@ __global__ void __launch_bounds__(kPairMax * kPairMax) k_small_strict_steps_pair
         pos[i] = p;
         vel[i] = v;
     }
+}
+
+// 32 < N <= 1024, one device: a cooperative grid of up to one CTA per SM, each
+// owning B = ceil(N / SMs) bodies, runs all `nsteps` in one launch.  Per step every
+// CTA (1) stages the time-t positions in shared memory, (2) evaluates the N terms
+// of each of its bodies with all its threads -- the sqrt/divide latency chains run
+// side by side -- (3) lets the owner thread add each row in ascending j, exactly
+// the reference's summation order, and (4) writes the new positions to the other
+// global buffer; one grid-wide barrier per step stands in for the reference's
+// two spin barriers (sim_gravity.c:1140, :1226).  Bit-identical to the reference.
+struct CoopParams {
+    double2      *pos[2];
+    double2      *vel;
+    const double *mass;
+    int           n;
+    int           bodies_per_cta;
+    int           cur;
+    double        dt;
+    long long     nsteps;
+};
+
+constexpr int kCoopThreads = 256;
+
+__host__ __device__ inline size_t coop_smem_bytes(int n, int bodies_per_cta)
+{
+    // s_pos[n] double2 | s_mass[n] double | s_term[B][n] double2 | s_drift[B] double2 | s_skip[B][n] u8
+    const size_t n_even = ((size_t)n + 1) & ~(size_t)1;      // keeps the double2 arrays 16-byte aligned
+    return (size_t)n * 16 + n_even * 8 + (size_t)bodies_per_cta * n * 16 + (size_t)bodies_per_cta * 16 +
+           (size_t)bodies_per_cta * n;
+}
+
+__global__ void __launch_bounds__(kCoopThreads) k_strict_coop_steps(const CoopParams P)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char coop_smem[];
+
+    const int n = P.n, B = P.bodies_per_cta, tid = threadIdx.x;
+    double2       *s_pos   = reinterpret_cast<double2 *>(coop_smem);
+    double        *s_mass  = reinterpret_cast<double *>(s_pos + n);
+    double2       *s_term  = reinterpret_cast<double2 *>(s_mass + ((n + 1) & ~1));
+    double2       *s_drift = s_term + (size_t)B * n;
+    unsigned char *s_skip  = reinterpret_cast<unsigned char *>(s_drift + B);
+
+    const int  b0    = blockIdx.x * B;
+    const int  nb    = min(B, n - b0);
+    const bool owner = tid < nb;                 // thread b owns body b0 + b
+    double2 p = make_double2(0.0, 0.0), v = make_double2(0.0, 0.0);
+    if (owner) {
+        p = P.pos[P.cur][b0 + tid];
+        v = P.vel[b0 + tid];
+    }
+    for (int j = tid; j < n; j += kCoopThreads) s_mass[j] = P.mass[j];
+
+    int cur = P.cur;
+    for (long long s = 0; s < P.nsteps; ++s) {
+        const double2 *src = P.pos[cur];
+        for (int j = tid; j < n; j += kCoopThreads) s_pos[j] = src[j];
+        if (owner) s_drift[tid] = make_double2(half_drift(p.x, v.x, P.dt), half_drift(p.y, v.y, P.dt));
+        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            const double2 d  = s_drift[b];
+            const int     gi = b0 + b;
+            for (int j = tid; j < n; j += kCoopThreads) {
+                const double dx = __dsub_rn(s_pos[j].x, d.x);
+                const double dy = __dsub_rn(s_pos[j].y, d.y);
+                const double r  = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                const bool skip = (j == gi) || (r == 0.0);   // sim_gravity.c:1191, :1199-1201
+                s_skip[(size_t)b * n + j] = skip ? 1 : 0;
+                if (!skip) {
+                    const double t = __ddiv_rn(s_mass[j], __dmul_rn(__dmul_rn(r, r), r));
+                    s_term[(size_t)b * n + j] = make_double2(__dmul_rn(t, dx), __dmul_rn(t, dy));
+                }
+            }
+        }
+        __syncthreads();
+        if (owner) {
+            const double2       *row  = s_term + (size_t)tid * n;
+            const unsigned char *skip = s_skip + (size_t)tid * n;
+            double sx = 0.0, sy = 0.0;
+            for (int j = 0; j < n; ++j) {
+                if (skip[j]) continue;
+                sx = __dadd_rn(sx, row[j].x);
+                sy = __dadd_rn(sy, row[j].y);
+            }
+            double ax, ay;
+            kick_drift(sx, P.dt, p.x, v.x, p.x, v.x, ax);
+            kick_drift(sy, P.dt, p.y, v.y, p.y, v.y, ay);
+            P.pos[cur ^ 1][b0 + tid] = p;
+        }
+        cur ^= 1;
+        grid.sync();
+    }
+    if (owner) P.vel[b0 + tid] = v;
 }
 
 // ---------------------------------------------------------------------------

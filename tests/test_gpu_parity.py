@@ -48,8 +48,11 @@ def test_strict_small_kernel_reproduces_reference_bits(name):
                 assert bits_equal(got, cp[key]), "%s step %d %s" % (name, done, key)
 
 
-@pytest.mark.parametrize("n", [1, 2, 129, 1500, 3000])
-def test_strict_rows_kernel_bits_vs_oracle(n):
+@pytest.mark.parametrize("n", [1, 2, 32, 33, 129, 200, 777, 1024, 1500, 3000])
+def test_strict_kernels_bits_vs_oracle(n):
+    """Every strict kernel shape: pair-parallel (N <= 32), cooperative multi-step
+    grid (N <= 1024), rows (any N); odd and even step batches so that the state
+    ends in either ping-pong buffer."""
     m, x, y, vx, vy = g.plummer(n, seed=3)
     with g.GravityCuda(n, kernel=g.KERNEL_STRICT) as h:
         h.upload(m, x, y, vx, vy)
@@ -57,8 +60,31 @@ def test_strict_rows_kernel_bits_vs_oracle(n):
         rax, ray = oracle.accel(m, x, y, vx, vy, 7, nthreads=NTHREADS)
         assert bits_equal(ax, rax) and bits_equal(ay, ray)
         h.step(7, 3)
+        ax, ay = h.accel(7)
+        h.step(7, 2)
+        h.step(7, 1)
         got = h.download()
-    want = oracle.step(m, x, y, vx, vy, 7, 3, nthreads=NTHREADS)
+    mid = oracle.step(m, x, y, vx, vy, 7, 3, nthreads=NTHREADS)
+    rax, ray = oracle.accel(m, *mid, 7, nthreads=NTHREADS)
+    assert bits_equal(ax, rax) and bits_equal(ay, ray)
+    want = oracle.step(m, *mid, 7, 3, nthreads=NTHREADS)
+    for a, b in zip(got, want):
+        assert bits_equal(a, b)
+
+
+def test_strict_200_bodies_with_coincident_pairs():
+    """The reference's MAX_OBJECT-sized case on the cooperative kernel, with exact
+    duplicates (r == 0 skip) and a massless body."""
+    n = 200
+    m, x, y, vx, vy = g.plummer(n, seed=21)
+    x[150], y[150], vx[150], vy[150] = x[3], y[3], vx[3], vy[3]
+    vx[3] = vy[3] = vx[150] = vy[150] = 0.0
+    m[77] = 0.0
+    with g.GravityCuda(n) as h:
+        h.upload(m, x, y, vx, vy)
+        h.step(60, 1001)
+        got = h.download()
+    want = oracle.step(m, x, y, vx, vy, 60, 1001)
     for a, b in zip(got, want):
         assert bits_equal(a, b)
 
@@ -99,6 +125,12 @@ def test_tiled_trajectory_1e4_steps(name):
     assert (np.hypot(vx - cp["vx_f"], vy - cp["vy_f"]) / vscale).max() <= TRAJ_TOL
     per_body = np.hypot(x - cp["x_f"], y - cp["y_f"]) / np.maximum(np.hypot(cp["x_f"], cp["y_f"]), 1e-300)
     assert np.median(per_body) <= TRAJ_TOL
+    # total energy drift after the 10^4 steps matches the reference's drift
+    m = fx["mass_f"]
+    e0 = sum(oracle.energy(*state0(fx)))
+    drift_ref = (sum(oracle.energy(m, cp["x_f"], cp["y_f"], cp["vx_f"], cp["vy_f"])) - e0) / abs(e0)
+    drift_gpu = (sum(oracle.energy(m, x, y, vx, vy)) - e0) / abs(e0)
+    assert abs(drift_gpu - drift_ref) <= TRAJ_TOL
 
 
 def test_tiled_rogue_star_1e5_steps_and_energy_drift():
@@ -190,6 +222,21 @@ def test_tiled_accel_config3_full_65536():
     e_gpu = rel_err_rows(ax[rows], ay[rows], tax, tay)
     e_ref = rel_err_rows(rax[rows], ray[rows], tax, tay)
     assert np.median(e_gpu) <= 2 * np.median(e_ref) + 1e-16
+
+
+def test_tiled_accel_config4_262144_row_sample():
+    """BASELINE.json configs[3] size: N = 262,144, parity on a 4,096-row subsample."""
+    n = 262144
+    m, x, y, vx, vy = g.plummer(n, seed=1)
+    with g.GravityCuda(n) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(1)
+    rows = np.arange(0, n, n // 4096, dtype=np.int64)
+    rax, ray = oracle.accel(m, x, y, vx, vy, 1, rows=rows, nthreads=NTHREADS)
+    pure = rel_err_rows(ax[rows], ay[rows], rax, ray)
+    floor = 0.1 * np.median(np.hypot(rax, ray))
+    assert (np.hypot(ax[rows] - rax, ay[rows] - ray) / np.maximum(np.hypot(rax, ray), floor)).max() <= ACCEL_TOL
+    assert (pure > ACCEL_TOL).sum() <= 1
 
 
 def test_tiled_coincident_bodies_take_the_guarded_path():
