@@ -93,7 +93,8 @@ void gravity_cuda_destroy(gravity_cuda_t *h);
 const char *gravity_cuda_last_error(const gravity_cuda_t *h);
 
 /* Options: "kernel" (GRAVITY_CUDA_KERNEL_*), "threads" (CTA size of the tiled
- * kernel: 128|256), "bodies_per_thread" (1|2|4), "ctas_per_sm" (1..8),
+ * kernel: 128|256), "bodies_per_thread" (1|2|4), "ctas_per_sm" (1..8) -- 0, the
+ * default, lets the library pick the shape that fills the SMs best for N,
  * "overlap" (0|1: start the local j-shard while the all-gather is in flight),
  * "exchange" (0: NCCL all-gather of the new positions, default; 1: peer-memory
  * stores + flags, see gravity_cuda_p2p_connect),

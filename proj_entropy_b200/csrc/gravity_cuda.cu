@@ -81,7 +81,8 @@ struct gravity_cuda {
     int cur = 0;                     // which pos[] holds time t
     bool uploaded = false, planned = false;
     int opt_kernel = GRAVITY_CUDA_KERNEL_AUTO;
-    int opt_threads = 256, opt_bpt = 4, opt_ctas_per_sm = 1, opt_overlap = 0, opt_mass_fold = 1;
+    int opt_threads = 0, opt_bpt = 0, opt_ctas_per_sm = 0;   // 0: chosen per problem size (build_plan)
+    int opt_overlap = 0, opt_mass_fold = 1;
     int opt_exchange = 0;            // 0: NCCL all-gather, 1: peer-memory stores + flags
     bool p2p_connected = false;
     unsigned long long step_id = 0;  // commits published so far (peer-memory exchange)
@@ -217,19 +218,49 @@ int build_plan(gravity_cuda_t *h)
 {
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
-        c.threads = h->opt_threads;
-        c.bpt = h->opt_bpt;
-        accum_kernel_t probe = pick_accum(c.threads, c.bpt, h->opt_ctas_per_sm);
+        const int n_tile = (int)((h->n + kTile - 1) / kTile);
+        if (h->opt_threads && h->opt_bpt) {
+            c.threads = h->opt_threads;
+            c.bpt = h->opt_bpt;
+            c.minb = c.threads == 256 ? (c.bpt == 4 ? 1 : 2) : (c.bpt == 4 ? 2 : 4);
+        } else {
+            // Pick the CTA shape by how well its work units fill one wave of CTAs.
+            // Bigger i-blocks amortise the j-tile loads over more pairs (measured
+            // relative pair rates below), smaller ones cut the quantisation loss
+            // when there are only a few units per CTA.
+            static const struct { int threads, bpt, ctas; double rate; } shapes[] = {
+                {256, 4, 1, 1.000}, {256, 2, 2, 0.974}, {128, 2, 4, 0.955}, {128, 1, 4, 0.905}};
+            double best = -1.0;
+            for (const auto &sh : shapes) {
+                const int64_t ib = sh.threads * sh.bpt;
+                const int64_t W = ((c.n_local + ib - 1) / ib) * n_tile;
+                const int64_t C = std::min<int64_t>(W, (int64_t)c.num_sms * sh.ctas);
+                if (W == 0) continue;
+                const double per = (double)W / (double)C;
+                // pairs a CTA really computes include the padding of a ragged last i-block
+                const double useful = (double)c.n_local / (double)(((c.n_local + ib - 1) / ib) * ib);
+                const double score = sh.rate * useful * per / std::ceil(per) *
+                                     std::min(1.0, (double)C * sh.threads / (c.num_sms * 256.0));
+                if (score > best) {
+                    best = score;
+                    c.threads = sh.threads;
+                    c.bpt = sh.bpt;
+                    if (!h->opt_ctas_per_sm) c.minb = sh.ctas;
+                }
+            }
+            if (best < 0) { c.threads = 256; c.bpt = 4; }
+        }
+        const int want_ctas = h->opt_ctas_per_sm ? h->opt_ctas_per_sm : (c.minb > 0 ? c.minb : 1);
+        accum_kernel_t probe = pick_accum(c.threads, c.bpt, want_ctas);
         if (!probe) return fail(h, "unsupported tiled kernel shape threads=%d bodies_per_thread=%d", c.threads, c.bpt);
         int occ = 0;
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe, c.threads, 0));
         if (occ < 1) return fail(h, "tiled kernel does not fit on an SM");
-        c.minb = std::min(occ, h->opt_ctas_per_sm);
+        c.minb = std::min(occ, want_ctas);
         const int max_cta = c.num_sms * c.minb;
 
         const int IB = c.threads * c.bpt;
         c.n_iblock = (int)((c.n_local + IB - 1) / IB);
-        const int n_tile = (int)((h->n + kTile - 1) / kTile);
 
         std::vector<Segment> segs;
         std::vector<int32_t> cta_begin;
@@ -770,13 +801,13 @@ int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
         if (value < 0 || value > 2) return fail(h, "kernel must be 0 (auto), 1 (tiled) or 2 (strict)");
         h->opt_kernel = (int)value;
     } else if (!strcmp(key, "threads")) {
-        if (value != 128 && value != 256) return fail(h, "threads must be 128 or 256");
+        if (value != 0 && value != 128 && value != 256) return fail(h, "threads must be 0 (auto), 128 or 256");
         h->opt_threads = (int)value;
     } else if (!strcmp(key, "bodies_per_thread")) {
-        if (value != 1 && value != 2 && value != 4) return fail(h, "bodies_per_thread must be 1, 2 or 4");
+        if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, "bodies_per_thread must be 0 (auto), 1, 2 or 4");
         h->opt_bpt = (int)value;
     } else if (!strcmp(key, "ctas_per_sm")) {
-        if (value < 1 || value > 8) return fail(h, "ctas_per_sm must be 1..8");
+        if (value < 0 || value > 8) return fail(h, "ctas_per_sm must be 0 (auto) or 1..8");
         h->opt_ctas_per_sm = (int)value;
     } else if (!strcmp(key, "overlap")) {
         h->opt_overlap = value ? 1 : 0;

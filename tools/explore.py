@@ -32,8 +32,11 @@ def main():
     for n in [int(s) for s in args.sizes.split(",")]:
         m, x, y, vx, vy = g.plummer(n, seed=1)
         for shape in args.shapes.split(","):
-            t, b, c = [int(v) for v in shape.split("x")]
-            with g.GravityCuda(n, kernel=g.KERNEL_TILED, threads=t, bodies_per_thread=b, ctas_per_sm=c) as h:
+            opts = {}
+            if shape != "auto":
+                t, b, c = [int(v) for v in shape.split("x")]
+                opts = dict(threads=t, bodies_per_thread=b, ctas_per_sm=c)
+            with g.GravityCuda(n, kernel=g.KERNEL_TILED, mass_fold=0, **opts) as h:
                 h.upload(m, x, y, vx, vy)
                 steps = max(1, min(args.steps, int(3e11 / (n * n)) + 1))
                 ms, kms = time_steps(h, 1, steps)
