@@ -38,6 +38,11 @@ METRIC = "fp64 pair-interactions/s"
 UNIT = "pairs/s"
 FLOPS_PER_PAIR = 20            # BASELINE.json north_star convention
 FP64_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 lanes x 2 x 1.965 GHz
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_tiled_accumulate<256,4,1> launch at the default
+# workload (N = 1,048,576 on one GPU), from the `ncu --set full` capture summarised in
+# profiles/r1_ncu_full_k_tiled_accumulate_1m_final_raw.csv; algorithmic bytes are 40*N = 41.9 MB
+# (positions, masses, velocities read once) plus the partial-sum rows.  Other configurations: not captured.
+NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, 1): 42436608 + 1720576}
 DT = 1
 
 
@@ -341,7 +346,8 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": 4 * 8 * n * world, "steps": e2e_steps, "checksum_x": checksum},
             "gpu_launches": total_launches,
             "roofline": {"bound": "fp64_fma_pipe", "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_tf if fp64_tf else None, "traffic": None,
+                         "frac": achieved / fp64_tf if fp64_tf else None,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((n, world)),
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry: "
                                         "keys %s)" % sorted(peaks.keys())[:4],
                          "peak_sm_mhz": fp64_mhz, "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,

@@ -69,6 +69,18 @@ int gravity_scenario_save(const gravity_scenario_t *s, const char *pathname);
 int gravity_plummer_generate(int64_t n, uint64_t seed, double *mass, double *x, double *y,
                              double *vx, double *vy);
 
+/* Binary snapshot of a running simulation: checkpoint / resume for any N (the
+ * reference has neither; its state lives only in RAM and re-selecting a scenario
+ * restarts from sim_time = 0, sim_gravity.c:415).  Layout, little endian:
+ * char magic[8] = "GRAVSNP1"; int64 n; int64 sim_time; int32 dt; int32 last_day;
+ * then mass, x, y, vx, vy as n doubles each.  read() allocates one block that
+ * the caller frees through *mass (x, y, vx, vy point into it). */
+int gravity_snapshot_write(const char *pathname, int64_t n, int64_t sim_time, int32_t dt, int32_t last_day,
+                           const double *mass, const double *x, const double *y,
+                           const double *vx, const double *vy);
+int gravity_snapshot_read(const char *pathname, int64_t *n, int64_t *sim_time, int32_t *dt, int32_t *last_day,
+                          double **mass, double **x, double **y, double **vx, double **vy);
+
 /* How many steps of size dt may run from sim_time before the reference would
  * take its next PATH sample: the commit at sim_gravity.c:1232-1236 samples the
  * just-committed positions when sim_time/86400 (taken BEFORE sim_time += DT,

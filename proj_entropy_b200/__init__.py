@@ -14,9 +14,10 @@ fallback: without the built CUDA library every call raises.
 """
 from .gravity import (GravityCuda, GravityError, KERNEL_AUTO, KERNEL_TILED, KERNEL_STRICT,
                       device_count, fp64_peak, nccl_unique_id, load_cuda_library)
-from .host import Scenario, ScenarioError, load_scenario, plummer, steps_until_day_change, load_host_library
+from .host import (Scenario, ScenarioError, load_scenario, plummer, steps_until_day_change, load_host_library,
+                   snapshot_read, snapshot_write)
 
 __all__ = ["GravityCuda", "GravityError", "KERNEL_AUTO", "KERNEL_TILED", "KERNEL_STRICT",
            "device_count", "fp64_peak", "nccl_unique_id", "load_cuda_library",
            "Scenario", "ScenarioError", "load_scenario", "plummer", "steps_until_day_change",
-           "load_host_library"]
+           "load_host_library", "snapshot_read", "snapshot_write"]

@@ -44,6 +44,12 @@ def load_host_library():
         "gravity_scenario_save": (C.c_int, [SP, C.c_char_p]),
         "gravity_plummer_generate": (C.c_int, [C.c_int64, C.c_uint64, _dp, _dp, _dp, _dp, _dp]),
         "gravity_steps_until_day_change": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+        "gravity_snapshot_write": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                             _dp, _dp, _dp, _dp, _dp]),
+        "gravity_snapshot_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                            C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp),
+                                            C.POINTER(_dp)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -116,3 +122,27 @@ def plummer(n, seed=1):
 
 def steps_until_day_change(sim_time, dt, last_day):
     return load_host_library().gravity_steps_until_day_change(int(sim_time), int(dt), int(last_day))
+
+
+def snapshot_write(pathname, sim_time, dt, last_day, mass, x, y, vx, vy):
+    lib = load_host_library()
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (mass, x, y, vx, vy)]
+    if lib.gravity_snapshot_write(os.fsencode(pathname), len(arrs[0]), int(sim_time), int(dt), int(last_day),
+                                  *[a.ctypes.data_as(_dp) for a in arrs]) != 0:
+        raise OSError("cannot write snapshot %s" % pathname)
+
+
+def snapshot_read(pathname):
+    """-> dict(n, sim_time, dt, last_day, mass, x, y, vx, vy)"""
+    lib = load_host_library()
+    n, t, dt, ld = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    ptrs = [_dp() for _ in range(5)]
+    if lib.gravity_snapshot_read(os.fsencode(pathname), C.byref(n), C.byref(t), C.byref(dt), C.byref(ld),
+                                 *[C.byref(p) for p in ptrs]) != 0:
+        raise OSError("cannot read snapshot %s" % pathname)
+    try:
+        cols = [np.ctypeslib.as_array(p, shape=(n.value,)).copy() for p in ptrs]
+    finally:
+        C.CDLL(None).free(C.cast(ptrs[0], C.c_void_p))
+    return dict(n=n.value, sim_time=t.value, dt=dt.value, last_day=ld.value, mass=cols[0], x=cols[1], y=cols[2],
+                vx=cols[3], vy=cols[4])

@@ -10,9 +10,9 @@
  * batched up to the next day boundary so that the PATH samples are taken at
  * exactly the commits at which the reference takes them.
  *
- * usage: gravity_headless (--scenario FILE | --plummer N [--seed S])
+ * usage: gravity_headless (--scenario FILE | --plummer N [--seed S] | --resume SNAPSHOT)
  *            [--steps K] [--dt SECONDS] [--gpus P] [--kernel auto|tiled|strict]
- *            [--checkpoint K1,K2,...] [--no-path] [--quiet]
+ *            [--checkpoint K1,K2,...] [--save SNAPSHOT] [--no-path] [--quiet]
  * prints one JSON line per checkpoint (body state as C99 hex floats) and a
  * final timing line.
  */
@@ -52,15 +52,16 @@ static void dump_state(const char *label, long long steps, const gravity_scenari
 static int usage(const char *argv0)
 {
     fprintf(stderr,
-            "usage: %s (--scenario FILE | --plummer N [--seed S]) [--steps K] [--dt SEC] [--gpus P]\n"
-            "          [--kernel auto|tiled|strict] [--checkpoint K1,K2,...] [--no-path] [--quiet]\n",
+            "usage: %s (--scenario FILE | --plummer N [--seed S] | --resume SNAPSHOT) [--steps K] [--dt SEC]\n"
+            "          [--gpus P] [--kernel auto|tiled|strict] [--checkpoint K1,K2,...] [--save SNAPSHOT]\n"
+            "          [--no-path] [--quiet]\n",
             argv0);
     return 2;
 }
 
 int main(int argc, char **argv)
 {
-    const char *scenario_file = NULL, *checkpoints = NULL, *kernel = "auto";
+    const char *scenario_file = NULL, *checkpoints = NULL, *kernel = "auto", *resume_file = NULL, *save_file = NULL;
     long long plummer_n = 0, steps = 1000, seed = 1, done = 0, next_cp;
     int dt_override = 0, gpus = 1, quiet = 0, want_path = 1, a, i;
     gravity_scenario_t *sim = NULL;
@@ -80,11 +81,13 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--gpus") && a + 1 < argc) gpus = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--kernel") && a + 1 < argc) kernel = argv[++a];
         else if (!strcmp(argv[a], "--checkpoint") && a + 1 < argc) checkpoints = argv[++a];
+        else if (!strcmp(argv[a], "--resume") && a + 1 < argc) resume_file = argv[++a];
+        else if (!strcmp(argv[a], "--save") && a + 1 < argc) save_file = argv[++a];
         else if (!strcmp(argv[a], "--no-path")) want_path = 0;
         else if (!strcmp(argv[a], "--quiet")) quiet = 1;
         else return usage(argv[0]);
     }
-    if ((scenario_file == NULL) == (plummer_n == 0)) return usage(argv[0]);
+    if ((scenario_file != NULL) + (plummer_n != 0) + (resume_file != NULL) != 1) return usage(argv[0]);
 
     /* ---- initial conditions (sim_gravity_init) ---- */
     if (scenario_file) {
@@ -94,6 +97,36 @@ int main(int argc, char **argv)
             gravity_scenario_free(sim);
             return 1;
         }
+    } else if (resume_file) {
+        int64_t rn = 0, rt = 0;
+        int32_t rdt = 0, rld = 0;
+        double *m, *x, *y, *vx, *vy;
+        if (gravity_snapshot_read(resume_file, &rn, &rt, &rdt, &rld, &m, &x, &y, &vx, &vy) != 0) {
+            fprintf(stderr, "ERROR cannot read snapshot '%s'\n", resume_file);
+            return 1;
+        }
+        sim = calloc(1, sizeof(*sim));
+        sim->n = (int32_t)rn;
+        sim->dt = rdt;
+        sim->sim_time = rt;
+        last_day = rld;
+        sim->sim_width = 50 * GRAVITY_AU;
+        snprintf(sim->sim_name, sizeof(sim->sim_name), "SNAPSHOT");
+        sim->mass = calloc((size_t)rn * 6, sizeof(double));
+        sim->radius = sim->mass + rn;
+        sim->x = sim->radius + rn;
+        sim->y = sim->x + rn;
+        sim->vx = sim->y + rn;
+        sim->vy = sim->vx + rn;
+        memcpy(sim->mass, m, sizeof(double) * (size_t)rn);
+        memcpy(sim->x, x, sizeof(double) * (size_t)rn);
+        memcpy(sim->y, y, sizeof(double) * (size_t)rn);
+        memcpy(sim->vx, vx, sizeof(double) * (size_t)rn);
+        memcpy(sim->vy, vy, sizeof(double) * (size_t)rn);
+        free(m);
+        sim->name = calloc((size_t)rn, GRAVITY_MAX_NAME);
+        sim->disp_color = calloc((size_t)rn * 2, sizeof(int32_t));
+        sim->max_path_disp_dflt = sim->disp_color + rn;
     } else {
         sim = calloc(1, sizeof(*sim));
         sim->n = (int32_t)plummer_n;
@@ -188,6 +221,14 @@ int main(int argc, char **argv)
     }
     t1 = microsec_now();
 
+    if (save_file) {
+        if (gravity_cuda_download(h, sim->x, sim->y, sim->vx, sim->vy) != 0 ||
+            gravity_snapshot_write(save_file, sim->n, sim->sim_time, sim->dt, last_day, sim->mass, sim->x, sim->y,
+                                   sim->vx, sim->vy) != 0) {
+            fprintf(stderr, "ERROR cannot write snapshot '%s'\n", save_file);
+            return 1;
+        }
+    }
     if (!quiet) {
         double secs = (double)(t1 - t0) / 1e6;
         double kin = 0, pot = 0;

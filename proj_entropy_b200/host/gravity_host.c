@@ -218,7 +218,7 @@ int gravity_scenario_load_ex(const char *pathname, int32_t inherit_dt, double in
 
         i = s->n;
         memset(s->name[i], 0, GRAVITY_MAX_NAME);
-        strncpy(s->name[i], name, GRAVITY_MAX_NAME - 1);
+        snprintf(s->name[i], GRAVITY_MAX_NAME, "%s", name);
         s->x[i]  = x + relto[idx - 1].x;                  /* :380-383 */
         s->y[i]  = y + relto[idx - 1].y;
         s->vx[i] = vx + relto[idx - 1].vx;
@@ -285,6 +285,67 @@ int64_t gravity_steps_until_day_change(int64_t sim_time, int32_t dt, int32_t las
     gap = boundary - sim_time;                    /* > 0 here */
     /* the commit of step s sees sim_time + (s-1)*dt */
     return (gap + dt - 1) / dt + 1;
+}
+
+/* ---- binary snapshots ----------------------------------------------------------- */
+
+static const char k_snap_magic[8] = {'G', 'R', 'A', 'V', 'S', 'N', 'P', '1'};
+
+int gravity_snapshot_write(const char *pathname, int64_t n, int64_t sim_time, int32_t dt, int32_t last_day,
+                           const double *mass, const double *x, const double *y,
+                           const double *vx, const double *vy)
+{
+    const double *cols[5] = {mass, x, y, vx, vy};
+    FILE *fp;
+    int c, ok = 1;
+    if (!pathname || n < 1 || !mass || !x || !y || !vx || !vy) return -1;
+    fp = fopen(pathname, "wb");
+    if (fp == NULL) return -1;
+    ok &= fwrite(k_snap_magic, 1, 8, fp) == 8;
+    ok &= fwrite(&n, sizeof(n), 1, fp) == 1;
+    ok &= fwrite(&sim_time, sizeof(sim_time), 1, fp) == 1;
+    ok &= fwrite(&dt, sizeof(dt), 1, fp) == 1;
+    ok &= fwrite(&last_day, sizeof(last_day), 1, fp) == 1;
+    for (c = 0; c < 5 && ok; c++) ok &= fwrite(cols[c], sizeof(double), (size_t)n, fp) == (size_t)n;
+    ok &= fclose(fp) == 0;
+    return ok ? 0 : -1;
+}
+
+int gravity_snapshot_read(const char *pathname, int64_t *n, int64_t *sim_time, int32_t *dt, int32_t *last_day,
+                          double **mass, double **x, double **y, double **vx, double **vy)
+{
+    char magic[8];
+    int64_t cnt = 0, t = 0;
+    int32_t d = 0, ld = 0;
+    double *block;
+    FILE *fp;
+    if (!pathname || !n || !sim_time || !dt || !last_day || !mass || !x || !y || !vx || !vy) return -1;
+    fp = fopen(pathname, "rb");
+    if (fp == NULL) return -1;
+    if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, k_snap_magic, 8) != 0 ||
+        fread(&cnt, sizeof(cnt), 1, fp) != 1 || fread(&t, sizeof(t), 1, fp) != 1 ||
+        fread(&d, sizeof(d), 1, fp) != 1 || fread(&ld, sizeof(ld), 1, fp) != 1 || cnt < 1 ||
+        cnt > ((int64_t)1 << 40)) {
+        fclose(fp);
+        return -1;
+    }
+    block = malloc(sizeof(double) * 5 * (size_t)cnt);
+    if (block == NULL || fread(block, sizeof(double), 5 * (size_t)cnt, fp) != 5 * (size_t)cnt) {
+        free(block);
+        fclose(fp);
+        return -1;
+    }
+    fclose(fp);
+    *n = cnt;
+    *sim_time = t;
+    *dt = d;
+    *last_day = ld;
+    *mass = block;
+    *x = block + cnt;
+    *y = block + 2 * cnt;
+    *vx = block + 3 * cnt;
+    *vy = block + 4 * cnt;
+    return 0;
 }
 
 /* ---- Plummer model ----------------------------------------------------------- */

@@ -96,3 +96,18 @@ def test_save_round_trip(tmp_path):
     assert t.n == s.n and t.dt == s.dt and t.sim_width == s.sim_width and t.names == s.names
     for k in ("mass", "radius", "x", "y", "vx", "vy"):
         assert bits_equal(getattr(s, k), getattr(t, k)), k      # %.17g round-trips doubles
+
+
+def test_snapshot_round_trip(tmp_path):
+    m, x, y, vx, vy = g.plummer(1234, seed=3)
+    p = tmp_path / "snap.bin"
+    g.snapshot_write(str(p), 86399, 7, 0, m, x, y, vx, vy)
+    s = g.snapshot_read(str(p))
+    assert (s["n"], s["sim_time"], s["dt"], s["last_day"]) == (1234, 86399, 7, 0)
+    for a, b in zip((m, x, y, vx, vy), (s["mass"], s["x"], s["y"], s["vx"], s["vy"])):
+        assert bits_equal(a, b)
+    assert os.path.getsize(p) == 8 + 8 + 8 + 4 + 4 + 5 * 8 * 1234
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"NOTASNAP" + bytes(64))
+    with pytest.raises(OSError):
+        g.snapshot_read(str(bad))
