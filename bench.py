@@ -56,12 +56,11 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(--steps, 5)")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--bodies-per-thread", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--exchange", type=int, default=1,
-                    help="multi-GPU position exchange: 0 = NCCL all-gather, 1 = peer-memory stores from the commit kernel")
+                    help="multi-GPU position exchange: 0 = NCCL all-gather, 1 = peer-memory stores from the step kernel")
     ap.add_argument("--mass-fold", type=int, default=0,
                     help="headline kernel path: 0 = general masses (13 FP64 instr/pair, default), 1 = let equal-mass "
                          "j-tiles take the 12-instruction path")
@@ -216,7 +215,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         nccl_id = ranks.broadcast_bytes(g.nccl_unique_id() if rank == 0 else None, 128)
 
-    opts = {"kernel": g.KERNEL_TILED, "overlap": args.overlap, "mass_fold": args.mass_fold}
+    opts = {"kernel": g.KERNEL_TILED, "mass_fold": args.mass_fold}
     if args.threads:
         opts["threads"] = args.threads
     if args.bodies_per_thread:
@@ -334,14 +333,14 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "planar Plummer model N=%d, DT=1 s, seed 1 (BASELINE.json configs[4] size)" % n,
-                       "bodies": n, "parallelism": "i-sharded x%d, %s" % (world, "peer-memory stores of the new positions from the commit "
+                       "bodies": n, "parallelism": "i-sharded x%d, %s" % (world, "peer-memory stores of the new positions from the step "
                                        "kernel + step flags" if exchange == 1 else
                                        "NCCL all-gather of positions per step"),
                        "l2": "compute-bound: 24*N bytes of j-state stream from L2/HBM per i-block, no flush needed; "
                              "inputs change every step",
                        "kernel": "tiled rsqrt, general masses, 13 FP64-pipe instr/pair" if not args.mass_fold else
                                  "tiled rsqrt, equal-mass tiles folded, 12 FP64-pipe instr/pair",
-                       "overlap": args.overlap, "mass_fold": args.mass_fold, "exchange": exchange},
+                       "mass_fold": args.mass_fold, "exchange": exchange},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 5 * 8 * n * world,
                     "d2h_bytes_per_step": 4 * 8 * n * world, "steps": e2e_steps, "checksum_x": checksum},

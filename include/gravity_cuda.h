@@ -75,10 +75,12 @@ int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nran
                              int device, const void *nccl_id, size_t id_bytes);
 
 /* Peer-memory exchange (option "exchange" = 1).  Instead of an NCCL all-gather,
- * the commit kernel stores each new position straight into every peer's copy
- * of the next position buffer over NVLink and publishes a step flag; the next
- * step's pair kernel waits for the flags.  Barrier B2 and the commit copy of the
- * reference (sim_gravity.c:1226, :1242-1245) thus cost no separate launch.
+ * the step kernel stores each new position, as soon as its i-block is finished,
+ * straight into every peer's copy of the next position buffer over NVLink and
+ * publishes a step flag when the shard is done; the next step's kernel fetches
+ * its own shard's j-tiles first and waits for the flags only when it reaches
+ * other ranks' tiles.  Barrier B2 and the commit copy of the reference
+ * (sim_gravity.c:1226, :1242-1245) thus cost no launch and overlap the math.
  * A single-process handle connects itself when the option is set.  Rank-mode
  * handles exchange one GRAVITY_CUDA_P2P_BLOB_BYTES blob per rank through the
  * host: export on every rank, all-gather the blobs in rank order, connect. */
@@ -95,7 +97,6 @@ const char *gravity_cuda_last_error(const gravity_cuda_t *h);
 /* Options: "kernel" (GRAVITY_CUDA_KERNEL_*), "threads" (CTA size of the tiled
  * kernel: 128|256), "bodies_per_thread" (1|2|4), "ctas_per_sm" (1..8) -- 0, the
  * default, lets the library pick the shape that fills the SMs best for N,
- * "overlap" (0|1: start the local j-shard while the all-gather is in flight),
  * "exchange" (0: NCCL all-gather of the new positions, default; 1: peer-memory
  * stores + flags, see gravity_cuda_p2p_connect),
  * "mass_fold" (0|1, default 1: j-tiles whose 256 masses are bit-identical are

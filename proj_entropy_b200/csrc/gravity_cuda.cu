@@ -29,9 +29,8 @@ struct DeviceCtx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t comm_stream = nullptr;
     ncclComm_t   comm = nullptr;
-    cudaEvent_t  ev_start = nullptr, ev_stop = nullptr, ev_commit = nullptr, ev_gather = nullptr;
+    cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;
 
     double2 *pos[2] = {nullptr, nullptr};
     double  *mass = nullptr;
@@ -57,12 +56,13 @@ struct DeviceCtx {
     int64_t i0 = 0;          // global index of local body 0
     int64_t n_local = 0;     // real bodies in this shard
 
-    // launch plan of the tiled kernel: up to two phases (local j-shard first,
-    // then the rest) when overlap is on, otherwise one.
+    // launch plan of the tiled kernel
     struct Phase { int n_cta = 0; int cta_seg_offset = 0; };
-    Phase phase[2];
-    int n_phase = 0;
+    Phase phase[1];
     int n_iblock = 0;
+    int local_tile_begin = 0, local_tile_end = 0;   // j-tiles of this rank's own shard
+    int32_t *iblock_arrivals = nullptr;             // [n_iblock], see k_tiled_accumulate
+    int32_t *iblocks_done = nullptr;
     int n_seg = 0;
     int threads = 0, bpt = 0, minb = 0;
 
@@ -82,13 +82,12 @@ struct gravity_cuda {
     bool uploaded = false, planned = false;
     int opt_kernel = GRAVITY_CUDA_KERNEL_AUTO;
     int opt_threads = 0, opt_bpt = 0, opt_ctas_per_sm = 0;   // 0: chosen per problem size (build_plan)
-    int opt_overlap = 0, opt_mass_fold = 1;
+    int opt_mass_fold = 1;
     int opt_exchange = 0;            // 0: NCCL all-gather, 1: peer-memory stores + flags
     bool p2p_connected = false;
     unsigned long long step_id = 0;  // commits published so far (peer-memory exchange)
     int64_t launches = 0;
     bool timing = false;
-    int64_t hot_launches = 0;
     char err[200] = "";
 };
 
@@ -264,31 +263,24 @@ int build_plan(gravity_cuda_t *h)
 
         std::vector<Segment> segs;
         std::vector<int32_t> cta_begin;
-        c.n_phase = 0;
-        if (h->opt_overlap && h->nranks > 1) {
-            // phase 0: tiles inside this rank's own shard (already local when the
-            // step starts); phase 1: everything else (needs the all-gather).
-            const int lt0 = (int)(c.i0 / kTile);
-            const int lt1 = (int)std::min<int64_t>(n_tile, (c.i0 + h->chunk) / kTile);
-            std::vector<int> local_runs = {lt0, std::max(lt0, lt1)};
-            std::vector<int> remote_runs;
-            if (lt0 > 0) { remote_runs.push_back(0); remote_runs.push_back(lt0); }
-            if (lt1 < n_tile) { remote_runs.push_back(std::max(lt0, lt1)); remote_runs.push_back(n_tile); }
-            if (remote_runs.empty()) { remote_runs.push_back(0); remote_runs.push_back(0); }
-            plan_phase(local_runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
-            plan_phase(remote_runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[1]);
-            c.n_phase = 2;
+        // Every i-block walks the j-tiles starting with this rank's own shard
+        // (already local when the step starts) and wraps around, so that the
+        // other ranks' positions are not needed until later in the kernel.
+        c.local_tile_begin = (int)std::min<int64_t>(n_tile, c.i0 / kTile);
+        c.local_tile_end = (int)std::min<int64_t>(n_tile, (c.i0 + h->chunk) / kTile);
+        std::vector<int> runs;
+        if (h->nranks > 1 && c.local_tile_begin > 0) {
+            runs = {c.local_tile_begin, n_tile, 0, c.local_tile_begin};
         } else {
-            std::vector<int> runs = {0, n_tile};
-            plan_phase(runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
-            c.n_phase = 1;
+            runs = {0, n_tile};
         }
+        plan_phase(runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
         c.n_seg = (int)segs.size();
 
-        // The commit kernel adds up the partial rows of one i-block in a fixed
-        // order.  Give every segment a partial row ("slot") such that the rows
-        // of one i-block are contiguous and ordered by (phase, CTA): a stable
-        // sort of the segment list on iblock.
+        // The CTA that finishes an i-block last adds up its partial rows in a
+        // fixed order.  Give every segment a partial row ("slot") such that the
+        // rows of one i-block are contiguous and ordered by CTA: a stable sort
+        // of the segment list on iblock.
         std::vector<int> order(segs.size());
         for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
         std::stable_sort(order.begin(), order.end(),
@@ -301,7 +293,13 @@ int build_plan(gravity_cuda_t *h)
         for (int b = 0; b < c.n_iblock; ++b) ib_begin[b + 1] += ib_begin[b];
 
         cudaFree(c.seg); cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin); cudaFree(c.partial);
+        cudaFree(c.iblock_arrivals); cudaFree(c.iblocks_done);
         c.seg = nullptr; c.cta_seg_begin = nullptr; c.iblock_seg_begin = nullptr; c.partial = nullptr;
+        c.iblock_arrivals = nullptr; c.iblocks_done = nullptr;
+        CUDA_TRY(h, cudaMalloc(&c.iblock_arrivals, sizeof(int32_t) * std::max(1, c.n_iblock)));
+        CUDA_TRY(h, cudaMalloc(&c.iblocks_done, sizeof(int32_t)));
+        CUDA_TRY(h, cudaMemset(c.iblock_arrivals, 0, sizeof(int32_t) * std::max(1, c.n_iblock)));
+        CUDA_TRY(h, cudaMemset(c.iblocks_done, 0, sizeof(int32_t)));
         CUDA_TRY(h, cudaMalloc(&c.seg, sizeof(Segment) * std::max<size_t>(1, segs.size())));
         CUDA_TRY(h, cudaMalloc(&c.cta_seg_begin, sizeof(int32_t) * std::max<size_t>(1, cta_begin.size())));
         CUDA_TRY(h, cudaMalloc(&c.iblock_seg_begin, sizeof(int32_t) * ib_begin.size()));
@@ -332,11 +330,50 @@ void hot_event(gravity_cuda_t *h, DeviceCtx &c)
 
 // ---- one step on every local device -----------------------------------------------
 
-int launch_tiled_phase(gravity_cuda_t *h, DeviceCtx &c, int phase, double dt)
+CommitParams commit_params(gravity_cuda_t *h, DeviceCtx &c, double dt, bool export_accel)
 {
-    const DeviceCtx::Phase &ph = c.phase[phase];
+    CommitParams P;
+    memset(&P, 0, sizeof(P));
+    P.pos_cur = c.pos[h->cur];
+    P.pos_next = c.pos[h->cur ^ 1];
+    P.vel = c.vel;
+    P.mass = c.mass;
+    P.partial = c.partial;
+    P.iblock_seg_begin = c.iblock_seg_begin;
+    P.iblock_arrivals = c.iblock_arrivals;
+    P.iblocks_done = c.iblocks_done;
+    P.n_iblock = c.n_iblock;
+    P.accel_out = c.accel;
+    P.n = h->n;
+    P.i_global0 = c.i0;
+    P.n_local = c.n_local;
+    P.iblock_size = c.threads * c.bpt;
+    P.export_accel = export_accel ? 1 : 0;
+    P.dt = dt;
+    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
+    P.wait_flags = p2p ? c.flags : nullptr;
+    P.wait_step = h->step_id;
+    P.px.enabled = (p2p && !export_accel) ? 1 : 0;
+    P.px.rank = c.rank;
+    P.px.nranks = h->nranks;
+    P.px.flags = c.flags;
+    P.px.commit_counter = c.commit_counter;
+    P.px.status = c.status;
+    P.px.step = h->step_id + 1;
+    for (int r = 0; r < h->nranks && r < kMaxPeers; ++r) {
+        P.px.peer_next[r] = c.peer_pos[h->cur ^ 1][r];
+        P.px.peer_flags[r] = c.peer_flags[r];
+    }
+    return P;
+}
+
+// The one launch of a tiled step: pairs, reduction, repair, kick + drift, hand-over.
+int launch_tiled(gravity_cuda_t *h, DeviceCtx &c, double dt, bool export_accel)
+{
+    const DeviceCtx::Phase &ph = c.phase[0];
     if (ph.n_cta == 0) return 0;
     AccumParams P;
+    memset(&P, 0, sizeof(P));
     P.pos = c.pos[h->cur];
     P.mass = c.mass;
     P.vel = c.vel;
@@ -353,49 +390,16 @@ int launch_tiled_phase(gravity_cuda_t *h, DeviceCtx &c, int phase, double dt)
     P.wait_step = h->step_id;
     P.wait_rank = c.rank;
     P.wait_nranks = h->nranks;
-    if (c.n_phase == 2 && phase == 0) P.wait_flags = nullptr;   // local j-tiles need no peer data
+    P.local_tile_begin = c.local_tile_begin;
+    P.local_tile_end = c.local_tile_end;
+    P.cm = commit_params(h, c, dt, export_accel);
     accum_kernel_t k = pick_accum(c.threads, c.bpt, c.minb);
     hot_event(h, c);
     k<<<ph.n_cta, c.threads, 0, c.stream>>>(P);
     hot_event(h, c);
     h->launches++;
-    if (&c == &h->ctx[0]) h->hot_launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
-}
-
-CommitParams commit_params(gravity_cuda_t *h, DeviceCtx &c, double dt, bool export_accel)
-{
-    CommitParams P;
-    P.pos_cur = c.pos[h->cur];
-    P.pos_next = c.pos[h->cur ^ 1];
-    P.vel = c.vel;
-    P.mass = c.mass;
-    P.partial = c.partial;
-    P.iblock_seg_begin = c.iblock_seg_begin;
-    P.accel_out = c.accel;
-    P.n = h->n;
-    P.i_global0 = c.i0;
-    P.n_local = c.n_local;
-    P.iblock_size = c.threads * c.bpt;
-    P.export_accel = export_accel ? 1 : 0;
-    P.dt = dt;
-    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
-    P.wait_flags = p2p ? c.flags : nullptr;
-    P.wait_step = h->step_id;
-    memset(&P.px, 0, sizeof(P.px));
-    P.px.enabled = (p2p && !export_accel) ? 1 : 0;
-    P.px.rank = c.rank;
-    P.px.nranks = h->nranks;
-    P.px.flags = c.flags;
-    P.px.commit_counter = c.commit_counter;
-    P.px.status = c.status;
-    P.px.step = h->step_id + 1;
-    for (int r = 0; r < h->nranks && r < kMaxPeers; ++r) {
-        P.px.peer_next[r] = c.peer_pos[h->cur ^ 1][r];
-        P.px.peer_flags[r] = c.peer_flags[r];
-    }
-    return P;
 }
 
 // Evaluate sim_gravity.c:1183-1222 once on all local devices, either advancing
@@ -406,29 +410,21 @@ int enqueue_evaluation(gravity_cuda_t *h, double dt, bool export_accel, bool gat
     if (kernel == GRAVITY_CUDA_KERNEL_TILED && !h->planned) {
         if (build_plan(h) != 0) return -1;
     }
+    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
         if (c.n_local == 0) {
             // an empty shard still has to tell its peers that it has nothing to send
-            if (h->opt_exchange == 1 && h->nranks > 1 && !export_accel) {
+            if (p2p && !export_accel) {
                 const CommitParams P = commit_params(h, c, dt, false);
-                k_commit_partials<<<1, kCommitThreads, 0, c.stream>>>(P);
+                k_publish_only<<<1, 32, 0, c.stream>>>(P.px);
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
             }
             continue;
         }
         if (kernel == GRAVITY_CUDA_KERNEL_TILED) {
-            if (launch_tiled_phase(h, c, 0, dt) != 0) return -1;
-            if (c.n_phase == 2) {
-                // remote tiles need the previous step's all-gather
-                CUDA_TRY(h, cudaStreamWaitEvent(c.stream, c.ev_gather, 0));
-                if (launch_tiled_phase(h, c, 1, dt) != 0) return -1;
-            }
-            const CommitParams P = commit_params(h, c, dt, export_accel);
-            const int grid = (int)((c.n_local + kCommitThreads - 1) / kCommitThreads);
-            k_commit_partials<<<grid, kCommitThreads, 0, c.stream>>>(P);
-            h->launches++;
+            if (launch_tiled(h, c, dt, export_accel) != 0) return -1;
         } else {
             const CommitParams P = commit_params(h, c, dt, export_accel);
             const int grid = (int)((c.n_local + kStrictThreads - 1) / kStrictThreads);
@@ -436,35 +432,21 @@ int enqueue_evaluation(gravity_cuda_t *h, double dt, bool export_accel, bool gat
             k_strict_rows<<<grid, kStrictThreads, 0, c.stream>>>(P);
             hot_event(h, c);
             h->launches++;
-            if (&c == &h->ctx[0]) h->hot_launches++;
+            CUDA_TRY(h, cudaGetLastError());
         }
-        CUDA_TRY(h, cudaGetLastError());
     }
-    if (!export_accel && gather_after && h->nranks > 1 && h->opt_exchange == 1) {
-        h->step_id++;      // the commit kernels stored into the peers and will publish this step
-    } else if (!export_accel && gather_after && h->nranks > 1) {
-        // barrier B2 + the NEXT_* -> state copy (sim_gravity.c:1226, :1242-1245)
-        // become one in-place all-gather of the new positions.
-        const bool two_stream = h->opt_overlap != 0;
-        if (two_stream) {
+    if (!export_accel && gather_after && h->nranks > 1) {
+        if (p2p) {
+            h->step_id++;      // the kernels stored into the peers and publish this step
+        } else {
+            // barrier B2 + the NEXT_* -> state copy (sim_gravity.c:1226, :1242-1245)
+            // become one in-place all-gather of the new positions.
+            NCCL_TRY(h, ncclGroupStart());
             for (DeviceCtx &c : h->ctx) {
-                CUDA_TRY(h, cudaSetDevice(c.device));
-                CUDA_TRY(h, cudaEventRecord(c.ev_commit, c.stream));
-                CUDA_TRY(h, cudaStreamWaitEvent(c.comm_stream, c.ev_commit, 0));
+                double2 *next = c.pos[h->cur ^ 1];
+                NCCL_TRY(h, ncclAllGather(next + c.i0, next, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
             }
-        }
-        NCCL_TRY(h, ncclGroupStart());
-        for (DeviceCtx &c : h->ctx) {
-            double2 *next = c.pos[h->cur ^ 1];
-            NCCL_TRY(h, ncclAllGather(next + c.i0, next, (size_t)h->chunk * 2, ncclDouble, c.comm,
-                                      two_stream ? c.comm_stream : c.stream));
-        }
-        NCCL_TRY(h, ncclGroupEnd());
-        if (two_stream) {
-            for (DeviceCtx &c : h->ctx) {
-                CUDA_TRY(h, cudaSetDevice(c.device));
-                CUDA_TRY(h, cudaEventRecord(c.ev_gather, c.comm_stream));
-            }
+            NCCL_TRY(h, ncclGroupEnd());
         }
     }
     if (!export_accel) h->cur ^= 1;
@@ -499,7 +481,6 @@ int sync_all(gravity_cuda_t *h)
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
         CUDA_TRY(h, cudaStreamSynchronize(c.stream));
-        CUDA_TRY(h, cudaStreamSynchronize(c.comm_stream));
     }
     return 0;
 }
@@ -517,28 +498,13 @@ int rank_barrier(gravity_cuda_t *h)
     return 0;
 }
 
-// with overlap the compute stream must not run ahead of the gather when the
-// caller reads positions or leaves the step loop
-int join_comm(gravity_cuda_t *h)
-{
-    if (!(h->opt_overlap && h->nranks > 1)) return 0;
-    for (DeviceCtx &c : h->ctx) {
-        CUDA_TRY(h, cudaSetDevice(c.device));
-        CUDA_TRY(h, cudaStreamWaitEvent(c.stream, c.ev_gather, 0));
-    }
-    return 0;
-}
-
 int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
 {
     CUDA_TRY(h, cudaSetDevice(c.device));
     CUDA_TRY(h, cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
     CUDA_TRY(h, cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreate(&c.ev_start));
     CUDA_TRY(h, cudaEventCreate(&c.ev_stop));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&c.ev_commit, cudaEventDisableTiming));
-    CUDA_TRY(h, cudaEventCreateWithFlags(&c.ev_gather, cudaEventDisableTiming));
     c.i0 = (int64_t)c.rank * h->chunk;
     c.n_local = std::max<int64_t>(0, std::min<int64_t>(h->chunk, h->n - c.i0));
     CUDA_TRY(h, cudaMalloc(&c.pos[0], sizeof(double2) * h->npad));
@@ -563,7 +529,6 @@ int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
         k_init_padding<<<(int)((npadding + 255) / 256), 256, 0, c.stream>>>(c.pos[0], c.pos[1], c.mass, h->n, h->npad);
         CUDA_TRY(h, cudaGetLastError());
     }
-    CUDA_TRY(h, cudaEventRecord(c.ev_gather, c.stream));
     CUDA_TRY(h, cudaStreamSynchronize(c.stream));
     return 0;
 }
@@ -692,7 +657,6 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
     for (DeviceCtx &c : h->ctx) {
         cudaSetDevice(c.device);
         if (c.stream) cudaStreamSynchronize(c.stream);
-        if (c.comm_stream) cudaStreamSynchronize(c.comm_stream);
         if (c.comm) ncclCommDestroy(c.comm);
         cudaFree(c.pos[0]); cudaFree(c.pos[1]); cudaFree(c.mass); cudaFree(c.vel); cudaFree(c.accel);
         cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.tile_mass);
@@ -705,13 +669,11 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
         }
         cudaFree(c.gather_tmp); cudaFree(c.flags); cudaFree(c.commit_counter); cudaFree(c.status); cudaFree(c.partial); cudaFree(c.seg);
         cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin);
+        cudaFree(c.iblock_arrivals); cudaFree(c.iblocks_done);
         for (cudaEvent_t e : c.kev) cudaEventDestroy(e);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_stop) cudaEventDestroy(c.ev_stop);
-        if (c.ev_commit) cudaEventDestroy(c.ev_commit);
-        if (c.ev_gather) cudaEventDestroy(c.ev_gather);
         if (c.stream) cudaStreamDestroy(c.stream);
-        if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
     }
     delete h;
 }
@@ -809,8 +771,6 @@ int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
     } else if (!strcmp(key, "ctas_per_sm")) {
         if (value < 0 || value > 8) return fail(h, "ctas_per_sm must be 0 (auto) or 1..8");
         h->opt_ctas_per_sm = (int)value;
-    } else if (!strcmp(key, "overlap")) {
-        h->opt_overlap = value ? 1 : 0;
     } else if (!strcmp(key, "mass_fold")) {
         h->opt_mass_fold = value ? 1 : 0;
     } else if (!strcmp(key, "exchange")) {
@@ -854,8 +814,7 @@ int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, 
             h->launches++;
         }
         CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, cudaEventRecord(c.ev_gather, c.stream));
-    }
+        }
     if (sync_all(h) != 0) return -1;
     h->uploaded = true;
     return 0;
@@ -865,7 +824,7 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
 {
     if (!h) return fail(nullptr, "download: NULL handle");
     if (!h->uploaded) return fail(h, "download before upload");
-    if (join_comm(h) != 0 || sync_all(h) != 0) return -1;
+    if (sync_all(h) != 0) return -1;
     const int64_t n = h->n, np = h->npad;
     if (x || y) {
         DeviceCtx &c = h->ctx[0];
@@ -953,7 +912,6 @@ int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
         }
         hot_event(h, c);
         h->launches++;
-        h->hot_launches++;
         CUDA_TRY(h, cudaGetLastError());
         return 0;
     }
@@ -966,7 +924,6 @@ int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
 int gravity_cuda_sync(gravity_cuda_t *h)
 {
     if (!h) return fail(nullptr, "sync: NULL handle");
-    if (join_comm(h) != 0) return -1;
     if (sync_all(h) != 0) return -1;
     return check_exchange_status(h);
 }
@@ -982,7 +939,6 @@ int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay)
     if (!h) return fail(nullptr, "accel: NULL handle");
     if (!h->uploaded) return fail(h, "accel before upload");
     if (!ax || !ay) return fail(h, "accel: NULL array");
-    if (join_comm(h) != 0) return -1;
     if (enqueue_evaluation(h, (double)dt, true, false) != 0) return -1;
     if (sync_all(h) != 0) return -1;
     const int64_t n = h->n, np = h->npad;
@@ -1048,7 +1004,6 @@ int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential)
 {
     if (!h) return fail(nullptr, "energy: NULL handle");
     if (!h->uploaded) return fail(h, "energy before upload");
-    if (join_comm(h) != 0) return -1;
     long double ke = 0, pe = 0;
     std::vector<double> buf;
     for (DeviceCtx &c : h->ctx) {
@@ -1100,9 +1055,8 @@ int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential)
 int gravity_cuda_timer_start(gravity_cuda_t *h)
 {
     if (!h) return fail(nullptr, "timer_start: NULL handle");
-    if (join_comm(h) != 0 || sync_all(h) != 0) return -1;
+    if (sync_all(h) != 0) return -1;
     h->timing = true;
-    h->hot_launches = 0;
     h->ctx[0].kev_used = 0;
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
@@ -1114,7 +1068,6 @@ int gravity_cuda_timer_start(gravity_cuda_t *h)
 int gravity_cuda_timer_stop(gravity_cuda_t *h, double *ms)
 {
     if (!h) return fail(nullptr, "timer_stop: NULL handle");
-    if (join_comm(h) != 0) return -1;
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
         CUDA_TRY(h, cudaEventRecord(c.ev_stop, c.stream));

@@ -20,6 +20,7 @@
 namespace gravity {
 
 constexpr int    kTile        = 256;     // j-bodies per shared-memory tile
+constexpr int    kPairsPerIteration = 16;
 constexpr int    kStages      = 4;       // tile ring depth
 constexpr int    kLookahead   = 2;       // tiles in flight ahead of the consumer
 constexpr int    kSmallMax    = 1024;    // largest N of the single-CTA kernel
@@ -53,6 +54,29 @@ struct Segment {
     int32_t slot;         // which partial[] row this segment writes
 };
 
+struct CommitParams {
+    const double2 *pos_cur;         // time-t positions (all bodies)
+    double2       *pos_next;        // time-t+1 positions (all bodies; we write our shard)
+    double2       *vel;             // local shard, updated in place
+    const double  *mass;
+    const double2 *partial;
+    const int32_t *iblock_seg_begin;    // [n_iblock + 1] partial rows of each i-block
+    int32_t       *iblock_arrivals;     // [n_iblock] segments finished so far (self-resetting)
+    int32_t       *iblocks_done;        // [1] i-blocks committed so far (self-resetting)
+    int32_t        n_iblock;
+    int32_t        reserved;
+    double2       *accel_out;       // local shard, used when export_accel
+    int64_t        n;               // real bodies, all shards
+    int64_t        i_global0;
+    int64_t        n_local;
+    int32_t        iblock_size;     // IB of the accumulate kernel
+    int32_t        export_accel;    // 1: write AX,AY and leave the state alone
+    double         dt;
+    const unsigned long long *wait_flags;   // strict kernel only: it reads pos_cur itself
+    unsigned long long wait_step;
+    PeerExchange   px;
+};
+
 struct AccumParams {
     const double2 *pos;             // time-t positions of all bodies
     const double  *mass;
@@ -65,29 +89,15 @@ struct AccumParams {
     int64_t        i_global0;       // global index of local body 0
     int64_t        n_local;         // real bodies in the local shard
     double         dt;              // (double)DT
-    const unsigned long long *wait_flags;   // NULL, or this rank's flag array
+    // peer-memory exchange: j-tiles outside [local_tile_begin, local_tile_end) hold
+    // other ranks' bodies and may only be fetched once every peer has published
+    // `wait_step`; NULL wait_flags = nothing to wait for
+    const unsigned long long *wait_flags;
     unsigned int  *wait_status;
     unsigned long long wait_step;
     int32_t        wait_rank, wait_nranks;
-};
-
-struct CommitParams {
-    const double2 *pos_cur;         // time-t positions (all bodies)
-    double2       *pos_next;        // time-t+1 positions (all bodies; we write our shard)
-    double2       *vel;             // local shard, updated in place
-    const double  *mass;
-    const double2 *partial;
-    const int32_t *iblock_seg_begin;    // [n_iblock + 1]
-    double2       *accel_out;       // local shard, used when export_accel
-    int64_t        n;               // real bodies, all shards
-    int64_t        i_global0;
-    int64_t        n_local;
-    int32_t        iblock_size;     // IB of the accumulate kernel
-    int32_t        export_accel;    // 1: write AX,AY and leave the state alone
-    double         dt;
-    const unsigned long long *wait_flags;   // strict kernel only: it reads pos_cur itself
-    unsigned long long wait_step;
-    PeerExchange   px;
+    int32_t        local_tile_begin, local_tile_end;
+    CommitParams   cm;              // what the last CTA to finish an i-block does with it
 };
 
 // ---------------------------------------------------------------------------
@@ -180,6 +190,25 @@ __device__ __forceinline__ void wait_for_peers(const unsigned long long *flags, 
     }
 }
 
+// The same wait done by ONE thread (the tile producer of the pair kernel, just
+// before it fetches the first tile that holds other ranks' bodies).
+__device__ __forceinline__ void wait_for_peers_one_thread(const unsigned long long *flags, unsigned long long step,
+                                                          int rank, int nranks, unsigned int *status)
+{
+    const long long t0 = clock64();
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) continue;
+        while (ld_acquire_sys(flags + r) < step) {
+            if (clock64() - t0 > kSpinTimeoutCycles) {
+                if (status) atomicExch(status, 1u);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 // Called by every thread of the commit grid after its stores: when the last CTA
 // gets here all new positions of this rank are visible system-wide and the step
 // number is published to every peer.
@@ -197,6 +226,15 @@ __device__ __forceinline__ void publish_to_peers(const PeerExchange &X)
                 if (r != X.rank) st_release_sys(X.peer_flags[r] + X.rank, X.step);
             }
         }
+    }
+}
+
+// One thread: publish this rank's step number in every peer's flag array.
+__device__ __forceinline__ void publish_step(const PeerExchange &X)
+{
+    __threadfence_system();
+    for (int r = 0; r < X.nranks; ++r) {
+        if (r != X.rank) st_release_sys(X.peer_flags[r] + X.rank, X.step);
     }
 }
 
@@ -281,9 +319,147 @@ __device__ __forceinline__ void kick_drift(double sum, double dt, double p, doub
 }
 
 // ---------------------------------------------------------------------------
+// Commit helpers: repair poisoned bodies, kick + drift, hand the result to the peers
+// ---------------------------------------------------------------------------
+
+// Guarded evaluation of one body by a whole CTA: the reference's own formula
+// per pair (sqrt, divide, both skips), lanes striding over j, fixed-shape tree
+// reduction (deterministic).  Only bodies whose fast sum came out non-finite
+// get here -- in practice bodies that coincide exactly with another body.
+__device__ inline void block_guarded_body(const CommitParams &P, int64_t gi, double px, double py,
+                                          double *s_red, double &sx, double &sy)
+{
+    double tx = 0.0, ty = 0.0;
+    for (int64_t j = threadIdx.x; j < P.n; j += blockDim.x) {
+        if (j == gi) continue;                            // sim_gravity.c:1191
+        const double2 pj = P.pos_cur[j];
+        pair_strict(pj.x, pj.y, P.mass[j], px, py, tx, ty);
+    }
+    s_red[threadIdx.x]              = tx;
+    s_red[blockDim.x + threadIdx.x] = ty;
+    __syncthreads();
+    for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            s_red[threadIdx.x]              += s_red[threadIdx.x + w];
+            s_red[blockDim.x + threadIdx.x] += s_red[blockDim.x + threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    sx = s_red[0];
+    sy = s_red[blockDim.x];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void commit_body(const CommitParams &P, int64_t li, double sx, double sy)
+{
+    const int64_t gi = P.i_global0 + li;
+    const double2 p  = P.pos_cur[gi];
+    const double2 v  = P.vel[li];
+    double nx, ny, nvx, nvy, ax, ay;
+    kick_drift(sx, P.dt, p.x, v.x, nx, nvx, ax);
+    kick_drift(sy, P.dt, p.y, v.y, ny, nvy, ay);
+    if (P.export_accel) {
+        P.accel_out[li] = make_double2(ax, ay);          // sim_gravity.c:1207-1208
+    } else {
+        const double2 pn = make_double2(nx, ny);
+        P.pos_next[gi] = pn;                             // NEXT_X, NEXT_Y  (:1218-1219)
+        P.vel[li]      = make_double2(nvx, nvy);         // NEXT_VX, NEXT_VY (:1220-1221)
+        if (P.px.enabled) {
+            // barrier B2 + the commit copy (:1226, :1242-1245): every peer gets
+            // the new position straight into its own pos_next over NVLink
+            for (int r = 0; r < P.px.nranks; ++r) {
+                if (r != P.px.rank) P.px.peer_next[r][gi] = pn;
+            }
+        }
+    }
+}
+
+// Executed by the whole CTA that finished an i-block last: add up the partial
+// rows in a fixed order (run-to-run deterministic), redo poisoned bodies on the
+// guarded path, kick + drift, store to self and peers, and publish the step when
+// this was the rank's last i-block.  Kept out of line so that it does not disturb
+// the register allocation of the pair loop.
+template <int THREADS, int R>
+__device__ __noinline__ void commit_iblock(const AccumParams &P, int iblock, double *s_red, int *s_bad, int *s_nbad)
+{
+    constexpr int IB  = THREADS * R;
+    const int     tid = threadIdx.x;
+    const int64_t li0 = (int64_t)iblock * IB;
+    const int     row0 = P.cm.iblock_seg_begin[iblock];
+    const int     row1 = P.cm.iblock_seg_begin[iblock + 1];
+    __threadfence();
+    if (tid == 0) P.cm.iblock_arrivals[iblock] = 0;              // ready for the next launch
+
+    double sx[R], sy[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        sx[r] = 0.0;
+        sy[r] = 0.0;
+        for (int row = row0; row < row1; ++row) {
+            const double2 part = __ldcg(P.partial + (size_t)row * IB + r * THREADS + tid);
+            sx[r] += part.x;
+            sy[r] += part.y;
+        }
+    }
+    bool any_bad = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t li = li0 + (int64_t)r * THREADS + tid;
+        any_bad = any_bad || (li < P.n_local && !(isfinite(sx[r]) && isfinite(sy[r])));
+    }
+    if (__syncthreads_or(any_bad)) {
+        if (P.wait_flags != nullptr) {
+            // the guarded path reads every body's position, also other ranks'
+            if (tid == 0) wait_for_peers_one_thread(P.wait_flags, P.wait_step, P.wait_rank, P.wait_nranks, P.wait_status);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t li  = li0 + (int64_t)r * THREADS + tid;
+            const bool    bad = li < P.n_local && !(isfinite(sx[r]) && isfinite(sy[r]));
+            if (tid == 0) *s_nbad = 0;
+            __syncthreads();
+            if (bad) s_bad[atomicAdd(s_nbad, 1)] = tid;
+            __syncthreads();
+            const int nbad = *s_nbad;
+            for (int b = 0; b < nbad; ++b) {
+                const int     owner = s_bad[b];
+                const int64_t oli   = li0 + (int64_t)r * THREADS + owner;
+                const int64_t ogi   = P.i_global0 + oli;
+                const double2 p     = P.pos[ogi];
+                const double2 v     = P.vel[oli];
+                double fx, fy;
+                block_guarded_body(P.cm, ogi, half_drift(p.x, v.x, P.dt), half_drift(p.y, v.y, P.dt), s_red, fx, fy);
+                if (tid == owner) {
+                    sx[r] = fx;
+                    sy[r] = fy;
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t li = li0 + (int64_t)r * THREADS + tid;
+        if (li < P.n_local) commit_body(P.cm, li, sx[r], sy[r]);
+    }
+    if (P.cm.px.enabled) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0 && atomicAdd(P.cm.iblocks_done, 1) == P.cm.n_iblock - 1) {
+            *P.cm.iblocks_done = 0;
+            publish_step(P.cm.px);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K1: tiled pair accumulation (the hot kernel)
 // ---------------------------------------------------------------------------
 //
+// ONE kernel per step: pair accumulation, reduction of the partial sums, the
+// guarded repair, kick + drift and -- sharded -- the hand-over of the new
+// positions to the peers all happen here.
 // Work = n_iblock x n_tile units (IB i-bodies against one j-tile).  The host
 // flattens the units i-block-major and gives each CTA an equal contiguous run
 // (a few Segments), so that one wave of SMs x ctas_per_sm CTAs finishes
@@ -298,7 +474,9 @@ __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, con
                                              double (&ax)[R], double (&ay)[R],
                                              const int64_t (&gi)[R], int64_t gj0)
 {
-#pragma unroll 4
+    // 16 pairs per unrolled iteration whatever R is (measured best for R = 2 and 4)
+    constexpr int kUnroll = kPairsPerIteration / R;
+#pragma unroll kUnroll
     for (int j = 0; j < kTile; ++j) {
         const double2 pj = sp[j];
         const double  mj = FOLD ? 0.0 : sm[j];
@@ -329,6 +507,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
     __shared__ alignas(128) double  s_mass[kStages][kTile];
     __shared__ alignas(8) uint64_t  s_full[kStages];
     __shared__ alignas(8) uint64_t  s_empty[kStages];
+    __shared__ double               s_red[2 * THREADS];   // guarded path only
+    __shared__ int                  s_bad[THREADS];
+    __shared__ int                  s_nbad, s_last;
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
@@ -344,10 +525,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
         mbar_fence_init();
     }
     __syncthreads();
-    wait_for_peers(P.wait_flags, P.wait_step, P.wait_rank, P.wait_nranks, P.wait_status);
 
     // producer cursor (meaningful in thread 0 only)
-    int p_seg = seg_begin, p_tile = 0, p_tile_end = 0, issued = 0;
+    int  p_seg = seg_begin, p_tile = 0, p_tile_end = 0, issued = 0;
+    bool peers_pending = P.wait_flags != nullptr;
     if (tid == 0 && p_seg < seg_end) {
         p_tile     = P.seg[p_seg].tile_begin;
         p_tile_end = P.seg[p_seg].tile_end;
@@ -356,6 +537,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
         if (p_seg >= seg_end) return;
         const int stage = issued % kStages;
         if (issued >= kStages) mbar_wait(&s_empty[stage], ((issued / kStages) - 1) & 1);
+        if (peers_pending && (p_tile < P.local_tile_begin || p_tile >= P.local_tile_end)) {
+            // first tile of other ranks' bodies: their stores of the previous step
+            // must have landed.  Tiles of this rank's own shard come first in every
+            // i-block's tile order, so the exchange hides behind them.
+            wait_for_peers_one_thread(P.wait_flags, P.wait_step, P.wait_rank, P.wait_nranks, P.wait_status);
+            peers_pending = false;
+        }
         mbar_arrive_expect_tx(&s_full[stage], kTileBytes);
         bulk_load(&s_pos[stage][0], P.pos + (size_t)p_tile * kTile, kTile * sizeof(double2), &s_full[stage]);
         bulk_load(&s_mass[stage][0], P.mass + (size_t)p_tile * kTile, kTile * sizeof(double), &s_full[stage]);
@@ -432,111 +620,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
         double2 *out = P.partial + (size_t)sg.slot * IB;
 #pragma unroll
         for (int r = 0; r < R; ++r) out[r * THREADS + tid] = make_double2(ax[r], ay[r]);
-    }
-}
 
-// ---------------------------------------------------------------------------
-// Commit: reduce the partials, repair poisoned bodies, kick + drift
-// ---------------------------------------------------------------------------
-
-// Guarded evaluation of one body by a whole CTA: the reference's own formula
-// per pair (sqrt, divide, both skips), lanes striding over j, fixed-shape tree
-// reduction (deterministic).  Only bodies whose fast sum came out non-finite
-// get here -- in practice bodies that coincide exactly with another body.
-__device__ inline void block_guarded_body(const CommitParams &P, int64_t gi, double px, double py,
-                                          double *s_red, double &sx, double &sy)
-{
-    double tx = 0.0, ty = 0.0;
-    for (int64_t j = threadIdx.x; j < P.n; j += blockDim.x) {
-        if (j == gi) continue;                            // sim_gravity.c:1191
-        const double2 pj = P.pos_cur[j];
-        pair_strict(pj.x, pj.y, P.mass[j], px, py, tx, ty);
-    }
-    s_red[threadIdx.x]              = tx;
-    s_red[blockDim.x + threadIdx.x] = ty;
-    __syncthreads();
-    for (int w = blockDim.x >> 1; w > 0; w >>= 1) {
-        if ((int)threadIdx.x < w) {
-            s_red[threadIdx.x]              += s_red[threadIdx.x + w];
-            s_red[blockDim.x + threadIdx.x] += s_red[blockDim.x + threadIdx.x + w];
+        // ---- the last CTA to finish a segment of this i-block commits it ----
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int rows = P.cm.iblock_seg_begin[sg.iblock + 1] - P.cm.iblock_seg_begin[sg.iblock];
+            s_last = (atomicAdd(P.cm.iblock_arrivals + sg.iblock, 1) == rows - 1) ? 1 : 0;
         }
         __syncthreads();
-    }
-    sx = s_red[0];
-    sy = s_red[blockDim.x];
-    __syncthreads();
-}
-
-__device__ __forceinline__ void commit_body(const CommitParams &P, int64_t li, double sx, double sy)
-{
-    const int64_t gi = P.i_global0 + li;
-    const double2 p  = P.pos_cur[gi];
-    const double2 v  = P.vel[li];
-    double nx, ny, nvx, nvy, ax, ay;
-    kick_drift(sx, P.dt, p.x, v.x, nx, nvx, ax);
-    kick_drift(sy, P.dt, p.y, v.y, ny, nvy, ay);
-    if (P.export_accel) {
-        P.accel_out[li] = make_double2(ax, ay);          // sim_gravity.c:1207-1208
-    } else {
-        const double2 pn = make_double2(nx, ny);
-        P.pos_next[gi] = pn;                             // NEXT_X, NEXT_Y  (:1218-1219)
-        P.vel[li]      = make_double2(nvx, nvy);         // NEXT_VX, NEXT_VY (:1220-1221)
-        if (P.px.enabled) {
-            // barrier B2 + the commit copy (:1226, :1242-1245): every peer gets
-            // the new position straight into its own pos_next over NVLink
-            for (int r = 0; r < P.px.nranks; ++r) {
-                if (r != P.px.rank) P.px.peer_next[r][gi] = pn;
-            }
-        }
+        if (s_last) commit_iblock<THREADS, R>(P, sg.iblock, s_red, s_bad, &s_nbad);
     }
 }
 
-constexpr int kCommitThreads = 256;
-
-__global__ void __launch_bounds__(kCommitThreads) k_commit_partials(const CommitParams P)
+// An empty shard still tells its peers that it has nothing to send.
+__global__ void k_publish_only(const PeerExchange X)
 {
-    __shared__ double  s_red[2 * kCommitThreads];
-    __shared__ int     s_bad[kCommitThreads];
-    __shared__ int     s_nbad;
-    __shared__ double2 s_fixed[kCommitThreads];
-
-    const int64_t li     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool    active = li < P.n_local;
-    double sx = 0.0, sy = 0.0;
-    if (active) {
-        const int64_t ib  = li / P.iblock_size;
-        const int64_t off = li - ib * P.iblock_size;
-        const int     s0  = P.iblock_seg_begin[ib];
-        const int     s1  = P.iblock_seg_begin[ib + 1];
-        for (int s = s0; s < s1; ++s) {                  // fixed order: deterministic
-            const double2 part = P.partial[(size_t)s * P.iblock_size + off];
-            sx += part.x;
-            sy += part.y;
-        }
-    }
-    if (threadIdx.x == 0) s_nbad = 0;
-    __syncthreads();
-    const bool bad = active && !(isfinite(sx) && isfinite(sy));
-    if (bad) s_bad[atomicAdd(&s_nbad, 1)] = threadIdx.x;
-    __syncthreads();
-    const int nbad = s_nbad;
-    for (int b = 0; b < nbad; ++b) {
-        const int     owner = s_bad[b];
-        const int64_t oli   = (int64_t)blockIdx.x * blockDim.x + owner;
-        const int64_t ogi   = P.i_global0 + oli;
-        const double2 p     = P.pos_cur[ogi];
-        const double2 v     = P.vel[oli];
-        double fx, fy;
-        block_guarded_body(P, ogi, half_drift(p.x, v.x, P.dt), half_drift(p.y, v.y, P.dt), s_red, fx, fy);
-        if (threadIdx.x == 0) s_fixed[owner] = make_double2(fx, fy);
-    }
-    __syncthreads();
-    if (bad) {
-        sx = s_fixed[threadIdx.x].x;
-        sy = s_fixed[threadIdx.x].y;
-    }
-    if (active) commit_body(P, li, sx, sy);
-    if (!P.export_accel) publish_to_peers(P.px);
+    if (threadIdx.x == 0 && blockIdx.x == 0) publish_step(X);
 }
 
 // ---------------------------------------------------------------------------

@@ -348,9 +348,9 @@ def test_full_size_1m_properties_and_row_sample():
 # ---------------------------------------------------------------------------
 
 @pytest.mark.multigpu
-@pytest.mark.parametrize("overlap,exchange", [(0, 0), (1, 0), (0, 1), (1, 1)])
-def test_two_gpus_agree_with_one(gpu_count, overlap, exchange):
-    """exchange=0: NCCL all-gather; exchange=1: the commit kernel stores into the
+@pytest.mark.parametrize("exchange", [0, 1])
+def test_two_gpus_agree_with_one(gpu_count, exchange):
+    """exchange=0: NCCL all-gather; exchange=1: the step kernel stores into the
     peer's position buffer over NVLink and publishes a step flag."""
     if gpu_count < 2:
         pytest.skip("needs 2 GPUs")
@@ -360,7 +360,7 @@ def test_two_gpus_agree_with_one(gpu_count, overlap, exchange):
         h1.upload(m, x, y, vx, vy)
         h1.step(5, 4)
         one = h1.download()
-    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_TILED, overlap=overlap, exchange=exchange) as h2:
+    with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_TILED, exchange=exchange) as h2:
         h2.upload(m, x, y, vx, vy)
         h2.step(5, 3)
         h2.accel(5)                      # an evaluation that must not disturb the exchange

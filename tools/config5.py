@@ -21,7 +21,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--bodies", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--rows", type=int, default=1024)
-ap.add_argument("--overlap", type=int, default=0)
 ap.add_argument("--mass-fold", type=int, default=0)
 ap.add_argument("--exchange", type=int, default=0)
 args = ap.parse_args()
@@ -31,7 +30,7 @@ n, dt = args.bodies, 1
 state = g.plummer(n, seed=1)
 nccl_id = ranks.broadcast_bytes(g.nccl_unique_id() if ranks.rank == 0 else None, 128) if ranks.world > 1 else None
 h = g.GravityCuda(n, rank=ranks.rank, nranks=ranks.world, device=ranks.local_rank, nccl_id=nccl_id,
-                  kernel=g.KERNEL_TILED, overlap=args.overlap, mass_fold=args.mass_fold)
+                  kernel=g.KERNEL_TILED, mass_fold=args.mass_fold)
 if ranks.world > 1 and args.exchange == 1:
     h.p2p_connect(ranks.all_gather_bytes(h.p2p_export()))
     h.set_option("exchange", 1)
@@ -85,7 +84,7 @@ if ranks.rank == 0:
         "hot_kernel_share_of_step_rank0": kms / ms if ms else None, "hot_kernel_launches_rank0": kl,
         "parity": [p0, p1],
         "energy": {"e0": ke0 + pe0, "e1": ke1 + pe1, "relative_drift": (ke1 + pe1 - ke0 - pe0) / abs(ke0 + pe0)},
-        "options": {"overlap": args.overlap, "mass_fold": args.mass_fold, "exchange": args.exchange},
+        "options": {"mass_fold": args.mass_fold, "exchange": args.exchange},
     }), flush=True)
 h.close()
 ranks.close()
