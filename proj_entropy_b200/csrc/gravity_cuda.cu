@@ -263,18 +263,36 @@ int build_plan(gravity_cuda_t *h)
 
         std::vector<Segment> segs;
         std::vector<int32_t> cta_begin;
-        // Every i-block walks the j-tiles starting with this rank's own shard
-        // (already local when the step starts) and wraps around, so that the
-        // other ranks' positions are not needed until later in the kernel.
+        // Every CTA first works through its share of (i-block, own-shard j-tile)
+        // units -- those bodies are already local when the step starts -- and only
+        // then through its share of the other ranks' tiles, so that the exchange
+        // of the previous step hides behind the first part.
         c.local_tile_begin = (int)std::min<int64_t>(n_tile, c.i0 / kTile);
         c.local_tile_end = (int)std::min<int64_t>(n_tile, (c.i0 + h->chunk) / kTile);
-        std::vector<int> runs;
-        if (h->nranks > 1 && c.local_tile_begin > 0) {
-            runs = {c.local_tile_begin, n_tile, 0, c.local_tile_begin};
+        if (h->nranks > 1) {
+            std::vector<int> local_runs = {c.local_tile_begin, c.local_tile_end};
+            std::vector<int> remote_runs;
+            if (c.local_tile_begin > 0) { remote_runs.push_back(0); remote_runs.push_back(c.local_tile_begin); }
+            if (c.local_tile_end < n_tile) { remote_runs.push_back(c.local_tile_end); remote_runs.push_back(n_tile); }
+            std::vector<Segment> seg_a, seg_b;
+            std::vector<int32_t> cta_a, cta_b;
+            DeviceCtx::Phase pa, pb;
+            plan_phase(local_runs, c.n_iblock, max_cta, seg_a, cta_a, pa);
+            if (remote_runs.empty()) { pb.n_cta = 0; cta_b.push_back(0); }
+            else plan_phase(remote_runs, c.n_iblock, max_cta, seg_b, cta_b, pb);
+            const int C = std::max(pa.n_cta, pb.n_cta);
+            for (int k = 0; k < C; ++k) {
+                cta_begin.push_back((int32_t)segs.size());
+                if (k < pa.n_cta) segs.insert(segs.end(), seg_a.begin() + cta_a[k], seg_a.begin() + cta_a[k + 1]);
+                if (k < pb.n_cta) segs.insert(segs.end(), seg_b.begin() + cta_b[k], seg_b.begin() + cta_b[k + 1]);
+            }
+            cta_begin.push_back((int32_t)segs.size());
+            c.phase[0].n_cta = C;
+            c.phase[0].cta_seg_offset = 0;
         } else {
-            runs = {0, n_tile};
+            std::vector<int> runs = {0, n_tile};
+            plan_phase(runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
         }
-        plan_phase(runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
         c.n_seg = (int)segs.size();
 
         // The CTA that finishes an i-block last adds up its partial rows in a

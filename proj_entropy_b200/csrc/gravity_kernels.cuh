@@ -209,32 +209,34 @@ __device__ __forceinline__ void wait_for_peers_one_thread(const unsigned long lo
     asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
-// Called by every thread of the commit grid after its stores: when the last CTA
-// gets here all new positions of this rank are visible system-wide and the step
-// number is published to every peer.
+// Called by every thread of a grid after its stores to the peers (strict rows
+// kernel): when the last CTA gets here all new positions of this rank are visible
+// system-wide and the step number is published to every peer, one lane per peer
+// so that the release stores travel over NVLink side by side.
 __device__ __forceinline__ void publish_to_peers(const PeerExchange &X)
 {
+    __shared__ int s_publish;
     if (!X.enabled) return;
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int prev = atomicAdd(X.commit_counter, 1u);
-        if (prev == gridDim.x - 1) {
-            *X.commit_counter = 0u;                      // ready for the next launch
-            __threadfence_system();
-            for (int r = 0; r < X.nranks; ++r) {
-                if (r != X.rank) st_release_sys(X.peer_flags[r] + X.rank, X.step);
-            }
-        }
+        s_publish = (prev == gridDim.x - 1) ? 1 : 0;
+        if (s_publish) *X.commit_counter = 0u;           // ready for the next launch
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_publish && (int)threadIdx.x < X.nranks && (int)threadIdx.x != X.rank) {
+        st_release_sys(X.peer_flags[threadIdx.x] + X.rank, X.step);
     }
 }
 
-// One thread: publish this rank's step number in every peer's flag array.
+// Lanes 0..nranks-1 of the calling CTA: publish this rank's step number in
+// every peer's flag array, one lane per peer.
 __device__ __forceinline__ void publish_step(const PeerExchange &X)
 {
-    __threadfence_system();
-    for (int r = 0; r < X.nranks; ++r) {
-        if (r != X.rank) st_release_sys(X.peer_flags[r] + X.rank, X.step);
+    if ((int)threadIdx.x < X.nranks && (int)threadIdx.x != X.rank) {
+        st_release_sys(X.peer_flags[threadIdx.x] + X.rank, X.step);
     }
 }
 
@@ -387,7 +389,6 @@ __device__ __noinline__ void commit_iblock(const AccumParams &P, int iblock, dou
     const int64_t li0 = (int64_t)iblock * IB;
     const int     row0 = P.cm.iblock_seg_begin[iblock];
     const int     row1 = P.cm.iblock_seg_begin[iblock + 1];
-    __threadfence();
     if (tid == 0) P.cm.iblock_arrivals[iblock] = 0;              // ready for the next launch
 
     double sx[R], sy[R];
@@ -444,12 +445,16 @@ __device__ __noinline__ void commit_iblock(const AccumParams &P, int iblock, dou
         if (li < P.n_local) commit_body(P.cm, li, sx[r], sy[r]);
     }
     if (P.cm.px.enabled) {
-        __threadfence_system();
+        // when this was the rank's last i-block, tell the peers
         __syncthreads();
-        if (tid == 0 && atomicAdd(P.cm.iblocks_done, 1) == P.cm.n_iblock - 1) {
-            *P.cm.iblocks_done = 0;
-            publish_step(P.cm.px);
+        if (tid == 0) {
+            __threadfence_system();          // this CTA's stores to the peers, before the count
+            *s_nbad = (atomicAdd(P.cm.iblocks_done, 1) == P.cm.n_iblock - 1) ? 1 : 0;
+            if (*s_nbad) *P.cm.iblocks_done = 0;
+            __threadfence();
         }
+        __syncthreads();
+        if (*s_nbad) publish_step(P.cm.px);
     }
 }
 
@@ -622,11 +627,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
         for (int r = 0; r < R; ++r) out[r * THREADS + tid] = make_double2(ax[r], ay[r]);
 
         // ---- the last CTA to finish a segment of this i-block commits it ----
-        __threadfence();
+        // (the CTA barrier orders every thread's row before thread 0's fence and
+        // arrival; one fence per CTA instead of one per thread)
         __syncthreads();
         if (tid == 0) {
             const int rows = P.cm.iblock_seg_begin[sg.iblock + 1] - P.cm.iblock_seg_begin[sg.iblock];
+            __threadfence();
             s_last = (atomicAdd(P.cm.iblock_arrivals + sg.iblock, 1) == rows - 1) ? 1 : 0;
+            __threadfence();
         }
         __syncthreads();
         if (s_last) commit_iblock<THREADS, R>(P, sg.iblock, s_red, s_bad, &s_nbad);
@@ -636,7 +644,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
 // An empty shard still tells its peers that it has nothing to send.
 __global__ void k_publish_only(const PeerExchange X)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) publish_step(X);
+    if (blockIdx.x == 0) publish_step(X);
 }
 
 // ---------------------------------------------------------------------------

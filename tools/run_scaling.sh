@@ -12,4 +12,4 @@ d=json.load(open("$OUT/scale_g${NG}_n${B}.json"))
 print("gpus=%d n=%d pairs/s=%.4g ms/step=%.3f frac_nominal=%.3f e2e=%.4g fold=%.4g" % (d["n_gpus"], d["config"]["bodies"], d["value"], d["ms_per_step"], d["roofline"]["job_frac_of_nominal"], d["e2e"]["value"], d.get("equal_mass_path",{}).get("value",0)))
 PY
 done
-run tools/config5.py 2>/dev/null | grep '^{' > $OUT/config5_g${NG}.json; cut -c1-600 $OUT/config5_g${NG}.json
+run tools/config5.py --exchange 1 2>/dev/null | grep '^{' > $OUT/config5_g${NG}.json; cut -c1-600 $OUT/config5_g${NG}.json
