@@ -170,31 +170,24 @@ accum_kernel_t pick_accum(int threads, int bpt, int minb)
 
 // ---- launch plan -------------------------------------------------------------
 
-// Flatten (i-block, j-tile) units i-block-major over the tile list `tiles`,
-// cut them into n_cta equal contiguous runs, and append the resulting segments.
-void plan_phase(const std::vector<int> &tile_runs /* pairs begin,end */, int n_iblock, int max_cta,
-                std::vector<Segment> &segs, std::vector<int32_t> &cta_begin, DeviceCtx::Phase &ph)
+// Units = (i-block, j-tile) pairs, flattened i-block-major over the tile list
+// `tile_runs` (pairs begin,end).  CTA c gets the units [bounds[c], bounds[c+1]);
+// the resulting segments are appended to `segs`, `cta_begin[c]` marks where CTA
+// c's segments start.
+void plan_units(const std::vector<int> &tile_runs, const std::vector<int64_t> &bounds,
+                std::vector<Segment> &segs, std::vector<int32_t> &cta_begin)
 {
     int64_t tiles_per_block = 0;
     for (size_t k = 0; k + 1 < tile_runs.size(); k += 2) tiles_per_block += tile_runs[k + 1] - tile_runs[k];
-    const int64_t W = (int64_t)n_iblock * tiles_per_block;
-    ph.cta_seg_offset = (int)cta_begin.size();
-    if (W == 0) {
-        ph.n_cta = 0;
-        cta_begin.push_back((int32_t)segs.size());
-        return;
-    }
-    const int C = (int)std::min<int64_t>(W, max_cta);
-    ph.n_cta = C;
+    const int C = (int)bounds.size() - 1;
     for (int c = 0; c < C; ++c) {
-        int64_t u = (W * c) / C;
-        const int64_t u1 = (W * (c + 1)) / C;
+        int64_t u = bounds[c];
+        const int64_t u1 = bounds[c + 1];
         cta_begin.push_back((int32_t)segs.size());
         while (u < u1) {
             const int ib = (int)(u / tiles_per_block);
             int64_t off = u % tiles_per_block;       // offset inside this block's tile list
-            // locate the run containing `off`
-            size_t k = 0;
+            size_t k = 0;                            // locate the run containing `off`
             while (off >= tile_runs[k + 1] - tile_runs[k]) {
                 off -= tile_runs[k + 1] - tile_runs[k];
                 k += 2;
@@ -211,6 +204,13 @@ void plan_phase(const std::vector<int> &tile_runs /* pairs begin,end */, int n_i
         }
     }
     cta_begin.push_back((int32_t)segs.size());
+}
+
+int64_t units_of(const std::vector<int> &tile_runs, int n_iblock)
+{
+    int64_t tiles_per_block = 0;
+    for (size_t k = 0; k + 1 < tile_runs.size(); k += 2) tiles_per_block += tile_runs[k + 1] - tile_runs[k];
+    return tiles_per_block * n_iblock;
 }
 
 int build_plan(gravity_cuda_t *h)
@@ -269,30 +269,37 @@ int build_plan(gravity_cuda_t *h)
         // of the previous step hides behind the first part.
         c.local_tile_begin = (int)std::min<int64_t>(n_tile, c.i0 / kTile);
         c.local_tile_end = (int)std::min<int64_t>(n_tile, (c.i0 + h->chunk) / kTile);
+        std::vector<int> local_runs, remote_runs;
         if (h->nranks > 1) {
-            std::vector<int> local_runs = {c.local_tile_begin, c.local_tile_end};
-            std::vector<int> remote_runs;
+            local_runs = {c.local_tile_begin, c.local_tile_end};
             if (c.local_tile_begin > 0) { remote_runs.push_back(0); remote_runs.push_back(c.local_tile_begin); }
             if (c.local_tile_end < n_tile) { remote_runs.push_back(c.local_tile_end); remote_runs.push_back(n_tile); }
-            std::vector<Segment> seg_a, seg_b;
-            std::vector<int32_t> cta_a, cta_b;
-            DeviceCtx::Phase pa, pb;
-            plan_phase(local_runs, c.n_iblock, max_cta, seg_a, cta_a, pa);
-            if (remote_runs.empty()) { pb.n_cta = 0; cta_b.push_back(0); }
-            else plan_phase(remote_runs, c.n_iblock, max_cta, seg_b, cta_b, pb);
-            const int C = std::max(pa.n_cta, pb.n_cta);
-            for (int k = 0; k < C; ++k) {
-                cta_begin.push_back((int32_t)segs.size());
-                if (k < pa.n_cta) segs.insert(segs.end(), seg_a.begin() + cta_a[k], seg_a.begin() + cta_a[k + 1]);
-                if (k < pb.n_cta) segs.insert(segs.end(), seg_b.begin() + cta_b[k], seg_b.begin() + cta_b[k + 1]);
-            }
-            cta_begin.push_back((int32_t)segs.size());
-            c.phase[0].n_cta = C;
-            c.phase[0].cta_seg_offset = 0;
         } else {
-            std::vector<int> runs = {0, n_tile};
-            plan_phase(runs, c.n_iblock, max_cta, segs, cta_begin, c.phase[0]);
+            local_runs = {0, n_tile};
         }
+        const int64_t Wa = units_of(local_runs, c.n_iblock), Wb = units_of(remote_runs, c.n_iblock);
+        const int C = (int)std::min<int64_t>(Wa + Wb, max_cta);
+        // CTA c gets an equal share of ALL units (difference at most one), made
+        // of its proportional share of the own-shard units plus whatever
+        // other-rank units fill it up.
+        std::vector<int64_t> bounds_a(C + 1, 0), bounds_b(C + 1, 0);
+        for (int k = 1; k <= C; ++k) {
+            bounds_a[k] = (Wa * k) / C;
+            bounds_b[k] = std::min(Wb, std::max(bounds_b[k - 1], ((Wa + Wb) * k) / C - bounds_a[k]));
+        }
+        if (C > 0) bounds_b[C] = Wb;
+        std::vector<Segment> seg_a, seg_b;
+        std::vector<int32_t> cta_a, cta_b;
+        if (C > 0) plan_units(local_runs, bounds_a, seg_a, cta_a);
+        if (C > 0 && Wb > 0) plan_units(remote_runs, bounds_b, seg_b, cta_b);
+        for (int k = 0; k < C; ++k) {
+            cta_begin.push_back((int32_t)segs.size());
+            segs.insert(segs.end(), seg_a.begin() + cta_a[k], seg_a.begin() + cta_a[k + 1]);
+            if (Wb > 0) segs.insert(segs.end(), seg_b.begin() + cta_b[k], seg_b.begin() + cta_b[k + 1]);
+        }
+        cta_begin.push_back((int32_t)segs.size());
+        c.phase[0].n_cta = C;
+        c.phase[0].cta_seg_offset = 0;
         c.n_seg = (int)segs.size();
 
         // The CTA that finishes an i-block last adds up its partial rows in a
