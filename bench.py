@@ -15,7 +15,7 @@ One JSON line on stdout (rank 0):
             CUDA events on the library's compute stream, max over ranks
   e2e       the same through the C ABI with HOST buffers: upload + step +
             download per step, wall clock
-  roofline  the tiled pair kernel against the FP64 FMA pipe (20 flops per pair,
+  roofline  the step kernel (pairs + reduction + kick/drift in one launch) against the FP64 FMA pipe (20 flops per pair,
             north_star's convention); the peak is measured in this run by a DFMA
             microbenchmark because MEASURED_PEAKS.json has no FP64 entry
   cpu_baseline  the reference's CPU loop (oracle port, bit-identical to the
@@ -38,11 +38,12 @@ METRIC = "fp64 pair-interactions/s"
 UNIT = "pairs/s"
 FLOPS_PER_PAIR = 20            # BASELINE.json north_star convention
 FP64_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 lanes x 2 x 1.965 GHz
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_tiled_accumulate<256,4,1> launch at the default
-# workload (N = 1,048,576 on one GPU), from the `ncu --set full` capture summarised in
-# profiles/r1_ncu_full_k_tiled_accumulate_1m_final_raw.csv; algorithmic bytes are 40*N = 41.9 MB
-# (positions, masses, velocities read once) plus the partial-sum rows.  Other configurations: not captured.
-NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, 1): 42436608 + 1720576}
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_tiled_accumulate<256,4,1> launch (= one whole step) at
+# the default workload (N = 1,048,576 on one GPU), from the `ncu --set full` capture summarised in
+# profiles/r1_ncu_full_k_tiled_accumulate_1m_final_raw.csv.  Algorithmic bytes are 72*N = 75.5 MB (positions,
+# masses, velocities read once: 40*N; new positions and velocities written: 32*N) plus the partial-sum rows.
+# Other configurations: not captured.
+NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, 1): 48045824 + 33719040}
 DT = 1
 
 
