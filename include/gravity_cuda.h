@@ -169,6 +169,16 @@ int gravity_cuda_kernel_times(gravity_cuda_t *h, double *ms_out, int64_t cap, in
  * (MHz, from the device's clock64 against the event time). */
 int gravity_cuda_fp64_peak(int device, double *tflops, double *sm_mhz);
 
+/* Host-only view of the tiled kernel's launch plan for rank `rank` of `nranks`
+ * on a device with `num_sms` SMs (threads/bpt/ctas_per_sm = 0: automatic).  No
+ * GPU is touched, so the planner can be checked anywhere.  info[10] receives
+ * {threads, bodies_per_thread, ctas_per_sm, n_cta, n_segments, n_iblock, n_tile,
+ *  local_tile_begin, local_tile_end, n_local}; seg_out (may be NULL) receives up to
+ * seg_cap rows of {cta, iblock, tile_begin, tile_end, partial_row} in the order the
+ * CTAs execute them. */
+int gravity_cuda_plan_probe(int64_t n, int nranks, int rank, int num_sms, int threads, int bpt, int ctas_per_sm,
+                            int32_t *info, int32_t *seg_out, int64_t seg_cap);
+
 /* Number of usable sm_100 devices, or a negative value. */
 int gravity_cuda_device_count(void);
 

@@ -213,109 +213,143 @@ int64_t units_of(const std::vector<int> &tile_runs, int n_iblock)
     return tiles_per_block * n_iblock;
 }
 
+// Everything about a launch plan that can be decided on the host without a GPU.
+struct HostPlan {
+    int threads = 0, bpt = 0, ctas = 0;              // CTA shape and CTAs per SM
+    int n_iblock = 0, n_tile = 0, n_cta = 0;
+    int local_tile_begin = 0, local_tile_end = 0;    // j-tiles of the rank's own shard
+    std::vector<Segment> segs;
+    std::vector<int32_t> cta_begin;                  // [n_cta + 1] into segs
+    std::vector<int32_t> ib_begin;                   // [n_iblock + 1] partial rows per i-block
+};
+
+// Pick the CTA shape by how well its work units fill one wave of CTAs.  Bigger
+// i-blocks amortise the j-tile loads over more pairs (measured relative pair
+// rates below); smaller ones cut the quantisation loss when there are only a
+// few units per CTA.  Explicit options win.
+void choose_shape(int64_t n_local, int n_tile, int num_sms, int opt_threads, int opt_bpt, int opt_ctas,
+                  int &threads, int &bpt, int &ctas)
+{
+    if (opt_threads && opt_bpt) {
+        threads = opt_threads;
+        bpt = opt_bpt;
+        ctas = threads == 256 ? (bpt == 4 ? 1 : 2) : (bpt == 4 ? 2 : 4);
+    } else {
+        static const struct { int threads, bpt, ctas; double rate; } shapes[] = {
+            {256, 4, 1, 1.000}, {256, 2, 2, 0.974}, {128, 2, 4, 0.955}, {128, 1, 4, 0.905}};
+        double best = -1.0;
+        threads = 256; bpt = 4; ctas = 1;
+        for (const auto &sh : shapes) {
+            const int64_t ib = sh.threads * sh.bpt;
+            const int64_t W = ((n_local + ib - 1) / ib) * n_tile;
+            if (W == 0) continue;
+            const int64_t C = std::min<int64_t>(W, (int64_t)num_sms * sh.ctas);
+            const double per = (double)W / (double)C;
+            // pairs a CTA really computes include the padding of a ragged last i-block
+            const double useful = (double)n_local / (double)(((n_local + ib - 1) / ib) * ib);
+            const double score = sh.rate * useful * per / std::ceil(per) *
+                                 std::min(1.0, (double)C * sh.threads / (num_sms * 256.0));
+            if (score > best) {
+                best = score;
+                threads = sh.threads;
+                bpt = sh.bpt;
+                ctas = sh.ctas;
+            }
+        }
+    }
+    if (opt_ctas) ctas = opt_ctas;
+}
+
+// Cut the (i-block, j-tile) units of one rank into per-CTA segment lists.
+void make_plan(int64_t n, int64_t n_local, int64_t i0, int64_t chunk, int nranks, int num_sms,
+               int threads, int bpt, int ctas, HostPlan &out)
+{
+    out.threads = threads;
+    out.bpt = bpt;
+    out.ctas = ctas;
+    const int IB = threads * bpt;
+    const int n_tile = (int)((n + kTile - 1) / kTile);
+    out.n_tile = n_tile;
+    out.n_iblock = (int)((n_local + IB - 1) / IB);
+    const int max_cta = num_sms * ctas;
+
+    // Every CTA first works through its share of (i-block, own-shard j-tile)
+    // units -- those bodies are already local when the step starts -- and only
+    // then through its share of the other ranks' tiles, so that the exchange
+    // of the previous step hides behind the first part.
+    out.local_tile_begin = (int)std::min<int64_t>(n_tile, i0 / kTile);
+    out.local_tile_end = (int)std::min<int64_t>(n_tile, (i0 + chunk) / kTile);
+    std::vector<int> local_runs, remote_runs;
+    if (nranks > 1) {
+        local_runs = {out.local_tile_begin, out.local_tile_end};
+        if (out.local_tile_begin > 0) { remote_runs.push_back(0); remote_runs.push_back(out.local_tile_begin); }
+        if (out.local_tile_end < n_tile) { remote_runs.push_back(out.local_tile_end); remote_runs.push_back(n_tile); }
+    } else {
+        local_runs = {0, n_tile};
+    }
+    const int64_t Wa = units_of(local_runs, out.n_iblock), Wb = units_of(remote_runs, out.n_iblock);
+    const int C = (int)std::min<int64_t>(Wa + Wb, max_cta);
+    out.n_cta = C;
+    // CTA c gets an equal share of ALL units (difference at most one), made of
+    // its proportional share of the own-shard units plus whatever other-rank
+    // units fill it up.
+    std::vector<int64_t> bounds_a(C + 1, 0), bounds_b(C + 1, 0);
+    for (int k = 1; k <= C; ++k) {
+        bounds_a[k] = (Wa * k) / C;
+        bounds_b[k] = std::min(Wb, std::max(bounds_b[k - 1], ((Wa + Wb) * k) / C - bounds_a[k]));
+    }
+    if (C > 0) bounds_b[C] = Wb;
+    std::vector<Segment> seg_a, seg_b;
+    std::vector<int32_t> cta_a, cta_b;
+    if (C > 0) plan_units(local_runs, bounds_a, seg_a, cta_a);
+    if (C > 0 && Wb > 0) plan_units(remote_runs, bounds_b, seg_b, cta_b);
+    out.segs.clear();
+    out.cta_begin.clear();
+    for (int k = 0; k < C; ++k) {
+        out.cta_begin.push_back((int32_t)out.segs.size());
+        out.segs.insert(out.segs.end(), seg_a.begin() + cta_a[k], seg_a.begin() + cta_a[k + 1]);
+        if (Wb > 0) out.segs.insert(out.segs.end(), seg_b.begin() + cta_b[k], seg_b.begin() + cta_b[k + 1]);
+    }
+    out.cta_begin.push_back((int32_t)out.segs.size());
+
+    // The CTA that finishes an i-block last adds up its partial rows in a fixed
+    // order.  Give every segment a partial row ("slot") such that the rows of
+    // one i-block are contiguous and ordered by CTA: a stable sort of the
+    // segment list on iblock.
+    std::vector<Segment> &segs = out.segs;
+    std::vector<int> order(segs.size());
+    for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].iblock < segs[b].iblock; });
+    for (size_t k = 0; k < order.size(); ++k) segs[order[k]].slot = (int32_t)k;
+    out.ib_begin.assign(out.n_iblock + 1, 0);
+    for (const Segment &sg : segs) out.ib_begin[sg.iblock + 1]++;
+    for (int b = 0; b < out.n_iblock; ++b) out.ib_begin[b + 1] += out.ib_begin[b];
+}
+
 int build_plan(gravity_cuda_t *h)
 {
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
         const int n_tile = (int)((h->n + kTile - 1) / kTile);
-        if (h->opt_threads && h->opt_bpt) {
-            c.threads = h->opt_threads;
-            c.bpt = h->opt_bpt;
-            c.minb = c.threads == 256 ? (c.bpt == 4 ? 1 : 2) : (c.bpt == 4 ? 2 : 4);
-        } else {
-            // Pick the CTA shape by how well its work units fill one wave of CTAs.
-            // Bigger i-blocks amortise the j-tile loads over more pairs (measured
-            // relative pair rates below), smaller ones cut the quantisation loss
-            // when there are only a few units per CTA.
-            static const struct { int threads, bpt, ctas; double rate; } shapes[] = {
-                {256, 4, 1, 1.000}, {256, 2, 2, 0.974}, {128, 2, 4, 0.955}, {128, 1, 4, 0.905}};
-            double best = -1.0;
-            for (const auto &sh : shapes) {
-                const int64_t ib = sh.threads * sh.bpt;
-                const int64_t W = ((c.n_local + ib - 1) / ib) * n_tile;
-                const int64_t C = std::min<int64_t>(W, (int64_t)c.num_sms * sh.ctas);
-                if (W == 0) continue;
-                const double per = (double)W / (double)C;
-                // pairs a CTA really computes include the padding of a ragged last i-block
-                const double useful = (double)c.n_local / (double)(((c.n_local + ib - 1) / ib) * ib);
-                const double score = sh.rate * useful * per / std::ceil(per) *
-                                     std::min(1.0, (double)C * sh.threads / (c.num_sms * 256.0));
-                if (score > best) {
-                    best = score;
-                    c.threads = sh.threads;
-                    c.bpt = sh.bpt;
-                    if (!h->opt_ctas_per_sm) c.minb = sh.ctas;
-                }
-            }
-            if (best < 0) { c.threads = 256; c.bpt = 4; }
-        }
-        const int want_ctas = h->opt_ctas_per_sm ? h->opt_ctas_per_sm : (c.minb > 0 ? c.minb : 1);
-        accum_kernel_t probe = pick_accum(c.threads, c.bpt, want_ctas);
-        if (!probe) return fail(h, "unsupported tiled kernel shape threads=%d bodies_per_thread=%d", c.threads, c.bpt);
+        int threads = 0, bpt = 0, ctas = 0;
+        choose_shape(c.n_local, n_tile, c.num_sms, h->opt_threads, h->opt_bpt, h->opt_ctas_per_sm, threads, bpt, ctas);
+        accum_kernel_t probe = pick_accum(threads, bpt, ctas);
+        if (!probe) return fail(h, "unsupported tiled kernel shape threads=%d bodies_per_thread=%d", threads, bpt);
         int occ = 0;
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe, c.threads, 0));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe, threads, 0));
         if (occ < 1) return fail(h, "tiled kernel does not fit on an SM");
-        c.minb = std::min(occ, want_ctas);
-        const int max_cta = c.num_sms * c.minb;
-
-        const int IB = c.threads * c.bpt;
-        c.n_iblock = (int)((c.n_local + IB - 1) / IB);
-
-        std::vector<Segment> segs;
-        std::vector<int32_t> cta_begin;
-        // Every CTA first works through its share of (i-block, own-shard j-tile)
-        // units -- those bodies are already local when the step starts -- and only
-        // then through its share of the other ranks' tiles, so that the exchange
-        // of the previous step hides behind the first part.
-        c.local_tile_begin = (int)std::min<int64_t>(n_tile, c.i0 / kTile);
-        c.local_tile_end = (int)std::min<int64_t>(n_tile, (c.i0 + h->chunk) / kTile);
-        std::vector<int> local_runs, remote_runs;
-        if (h->nranks > 1) {
-            local_runs = {c.local_tile_begin, c.local_tile_end};
-            if (c.local_tile_begin > 0) { remote_runs.push_back(0); remote_runs.push_back(c.local_tile_begin); }
-            if (c.local_tile_end < n_tile) { remote_runs.push_back(c.local_tile_end); remote_runs.push_back(n_tile); }
-        } else {
-            local_runs = {0, n_tile};
-        }
-        const int64_t Wa = units_of(local_runs, c.n_iblock), Wb = units_of(remote_runs, c.n_iblock);
-        const int C = (int)std::min<int64_t>(Wa + Wb, max_cta);
-        // CTA c gets an equal share of ALL units (difference at most one), made
-        // of its proportional share of the own-shard units plus whatever
-        // other-rank units fill it up.
-        std::vector<int64_t> bounds_a(C + 1, 0), bounds_b(C + 1, 0);
-        for (int k = 1; k <= C; ++k) {
-            bounds_a[k] = (Wa * k) / C;
-            bounds_b[k] = std::min(Wb, std::max(bounds_b[k - 1], ((Wa + Wb) * k) / C - bounds_a[k]));
-        }
-        if (C > 0) bounds_b[C] = Wb;
-        std::vector<Segment> seg_a, seg_b;
-        std::vector<int32_t> cta_a, cta_b;
-        if (C > 0) plan_units(local_runs, bounds_a, seg_a, cta_a);
-        if (C > 0 && Wb > 0) plan_units(remote_runs, bounds_b, seg_b, cta_b);
-        for (int k = 0; k < C; ++k) {
-            cta_begin.push_back((int32_t)segs.size());
-            segs.insert(segs.end(), seg_a.begin() + cta_a[k], seg_a.begin() + cta_a[k + 1]);
-            if (Wb > 0) segs.insert(segs.end(), seg_b.begin() + cta_b[k], seg_b.begin() + cta_b[k + 1]);
-        }
-        cta_begin.push_back((int32_t)segs.size());
-        c.phase[0].n_cta = C;
+        HostPlan plan;
+        make_plan(h->n, c.n_local, c.i0, h->chunk, h->nranks, c.num_sms, threads, bpt, std::min(occ, ctas), plan);
+        c.threads = plan.threads;
+        c.bpt = plan.bpt;
+        c.minb = plan.ctas;
+        c.n_iblock = plan.n_iblock;
+        c.local_tile_begin = plan.local_tile_begin;
+        c.local_tile_end = plan.local_tile_end;
+        c.phase[0].n_cta = plan.n_cta;
         c.phase[0].cta_seg_offset = 0;
-        c.n_seg = (int)segs.size();
-
-        // The CTA that finishes an i-block last adds up its partial rows in a
-        // fixed order.  Give every segment a partial row ("slot") such that the
-        // rows of one i-block are contiguous and ordered by CTA: a stable sort
-        // of the segment list on iblock.
-        std::vector<int> order(segs.size());
-        for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int a, int b) { return segs[a].iblock < segs[b].iblock; });
-        std::vector<int32_t> slot_of(segs.size());
-        for (size_t k = 0; k < order.size(); ++k) slot_of[order[k]] = (int32_t)k;
-        for (size_t k = 0; k < segs.size(); ++k) segs[k].slot = slot_of[k];
-        std::vector<int32_t> ib_begin(c.n_iblock + 1, 0);
-        for (const Segment &s : segs) ib_begin[s.iblock + 1]++;
-        for (int b = 0; b < c.n_iblock; ++b) ib_begin[b + 1] += ib_begin[b];
+        c.n_seg = (int)plan.segs.size();
+        const int IB = c.threads * c.bpt;
 
         cudaFree(c.seg); cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin); cudaFree(c.partial);
         cudaFree(c.iblock_arrivals); cudaFree(c.iblocks_done);
@@ -325,14 +359,14 @@ int build_plan(gravity_cuda_t *h)
         CUDA_TRY(h, cudaMalloc(&c.iblocks_done, sizeof(int32_t)));
         CUDA_TRY(h, cudaMemset(c.iblock_arrivals, 0, sizeof(int32_t) * std::max(1, c.n_iblock)));
         CUDA_TRY(h, cudaMemset(c.iblocks_done, 0, sizeof(int32_t)));
-        CUDA_TRY(h, cudaMalloc(&c.seg, sizeof(Segment) * std::max<size_t>(1, segs.size())));
-        CUDA_TRY(h, cudaMalloc(&c.cta_seg_begin, sizeof(int32_t) * std::max<size_t>(1, cta_begin.size())));
-        CUDA_TRY(h, cudaMalloc(&c.iblock_seg_begin, sizeof(int32_t) * ib_begin.size()));
-        CUDA_TRY(h, cudaMalloc(&c.partial, sizeof(double2) * std::max<size_t>(1, segs.size()) * IB));
-        CUDA_TRY(h, cudaMemcpy(c.seg, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice));
-        CUDA_TRY(h, cudaMemcpy(c.cta_seg_begin, cta_begin.data(), sizeof(int32_t) * cta_begin.size(),
+        CUDA_TRY(h, cudaMalloc(&c.seg, sizeof(Segment) * std::max<size_t>(1, plan.segs.size())));
+        CUDA_TRY(h, cudaMalloc(&c.cta_seg_begin, sizeof(int32_t) * std::max<size_t>(1, plan.cta_begin.size())));
+        CUDA_TRY(h, cudaMalloc(&c.iblock_seg_begin, sizeof(int32_t) * plan.ib_begin.size()));
+        CUDA_TRY(h, cudaMalloc(&c.partial, sizeof(double2) * std::max<size_t>(1, plan.segs.size()) * IB));
+        CUDA_TRY(h, cudaMemcpy(c.seg, plan.segs.data(), sizeof(Segment) * plan.segs.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(c.cta_seg_begin, plan.cta_begin.data(), sizeof(int32_t) * plan.cta_begin.size(),
                                cudaMemcpyHostToDevice));
-        CUDA_TRY(h, cudaMemcpy(c.iblock_seg_begin, ib_begin.data(), sizeof(int32_t) * ib_begin.size(),
+        CUDA_TRY(h, cudaMemcpy(c.iblock_seg_begin, plan.ib_begin.data(), sizeof(int32_t) * plan.ib_begin.size(),
                                cudaMemcpyHostToDevice));
     }
     h->planned = true;
@@ -1142,6 +1176,36 @@ int gravity_cuda_kernel_times(gravity_cuda_t *h, double *ms_out, int64_t cap, in
         }
     }
     if (count) *count = k;
+    return 0;
+}
+
+int gravity_cuda_plan_probe(int64_t n, int nranks, int rank, int num_sms, int threads, int bpt, int ctas_per_sm,
+                            int32_t *info, int32_t *seg_out, int64_t seg_cap)
+{
+    if (n < 1 || nranks < 1 || rank < 0 || rank >= nranks || num_sms < 1 || !info)
+        return fail(nullptr, "plan_probe: bad argument");
+    gravity_cuda geo;
+    set_geometry(&geo, n, nranks);
+    const int64_t i0 = (int64_t)rank * geo.chunk;
+    const int64_t n_local = std::max<int64_t>(0, std::min<int64_t>(geo.chunk, n - i0));
+    int t = 0, b = 0, c = 0;
+    choose_shape(n_local, (int)((n + kTile - 1) / kTile), num_sms, threads, bpt, ctas_per_sm, t, b, c);
+    if (!pick_accum(t, b, c)) return fail(nullptr, "plan_probe: unsupported shape %dx%d", t, b);
+    HostPlan plan;
+    make_plan(n, n_local, i0, geo.chunk, nranks, num_sms, t, b, c, plan);
+    const int32_t vals[10] = {plan.threads, plan.bpt, plan.ctas, plan.n_cta, (int32_t)plan.segs.size(), plan.n_iblock,
+                              plan.n_tile, plan.local_tile_begin, plan.local_tile_end, (int32_t)n_local};
+    memcpy(info, vals, sizeof(vals));
+    if (seg_out) {
+        for (int k = 0; k < plan.n_cta; ++k) {
+            for (int sidx = plan.cta_begin[k]; sidx < plan.cta_begin[k + 1]; ++sidx) {
+                if (sidx >= seg_cap) break;
+                const Segment &sg = plan.segs[sidx];
+                int32_t *o = seg_out + (size_t)sidx * 5;
+                o[0] = k; o[1] = sg.iblock; o[2] = sg.tile_begin; o[3] = sg.tile_end; o[4] = sg.slot;
+            }
+        }
+    }
     return 0;
 }
 

@@ -61,6 +61,8 @@ def load_cuda_library():
         "gravity_cuda_launch_count": (C.c_int, [H, C.POINTER(C.c_int64)]),
         "gravity_cuda_kernel_time": (C.c_int, [H, _dp, C.POINTER(C.c_int64)]),
         "gravity_cuda_kernel_times": (C.c_int, [H, _dp, C.c_int64, C.POINTER(C.c_int64)]),
+        "gravity_cuda_plan_probe": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64]),
         "gravity_cuda_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
     }
     for name, (res, args) in sigs.items():
@@ -102,6 +104,23 @@ def fp64_peak(device=0):
     if lib.gravity_cuda_fp64_peak(device, C.byref(tf), C.byref(mhz)) != 0:
         raise GravityError(lib.gravity_cuda_last_error(None).decode())
     return tf.value, mhz.value
+
+
+def plan_probe(n, nranks=1, rank=0, num_sms=148, threads=0, bodies_per_thread=0, ctas_per_sm=0):
+    """The tiled kernel's launch plan, computed on the host (no GPU needed).
+    Returns (info dict, segments array [n_segments, 5] = cta, iblock, tile_begin, tile_end, partial_row)."""
+    lib = load_cuda_library()
+    info = np.zeros(10, dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    if lib.gravity_cuda_plan_probe(n, nranks, rank, num_sms, threads, bodies_per_thread, ctas_per_sm,
+                                   info.ctypes.data_as(ip), None, 0) != 0:
+        raise GravityError(lib.gravity_cuda_last_error(None).decode())
+    segs = np.zeros((max(1, int(info[4])), 5), dtype=np.int32)
+    lib.gravity_cuda_plan_probe(n, nranks, rank, num_sms, threads, bodies_per_thread, ctas_per_sm,
+                                info.ctypes.data_as(ip), segs.ctypes.data_as(ip), int(info[4]))
+    keys = ["threads", "bodies_per_thread", "ctas_per_sm", "n_cta", "n_segments", "n_iblock", "n_tile",
+            "local_tile_begin", "local_tile_end", "n_local"]
+    return dict(zip(keys, (int(v) for v in info))), segs[:int(info[4])]
 
 
 class GravityCuda:
