@@ -12,6 +12,19 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 REFERENCE_DIR = "/root/reference"          # exists only in the build container
 
 
+def _ensure_built():
+    """The native artefacts are built in-tree by `make` / __graft_entry__.build()
+    and travel with the snapshot; if one is missing (fresh checkout), build it."""
+    import subprocess
+    needed = [os.path.join(ROOT, "proj_entropy_b200", f) for f in
+              ("libgravity_cuda.so", "libgravity_host.so", "gravity_headless")] + [os.path.join(ROOT, "oracle", "liboracle.so")]
+    if not all(os.path.exists(p) for p in needed):
+        subprocess.run(["make", "-C", ROOT, "all"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+_ensure_built()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
     config.addinivalue_line("markers", "multigpu: needs at least 2 GPUs")
