@@ -29,11 +29,12 @@ constexpr double kPadCoord    = 1.0e150;     // parking spot of padding bodies
 constexpr int    kMaxPeers    = 16;          // ranks of the peer-memory exchange
 constexpr long long kSpinTimeoutCycles = 20000000000LL;   // ~10 s: give up instead of hanging
 
-// Peer-memory exchange (replaces the NCCL all-gather when connected): the commit
+// Peer-memory exchange (replaces the NCCL all-gather when connected): the step
 // kernel stores every new position into each peer's copy of pos_next over
-// NVLink and, when its last CTA is done, publishes its step number in each
-// peer's flag array; the next step's pair kernel waits until every peer's flag
-// has reached the step it is about to read.
+// NVLink as soon as its i-block is committed and, when the rank's last i-block
+// is done, publishes its step number in each peer's flag array; the next step's
+// kernel waits, just before it fetches the first tile of other ranks' bodies,
+// until every peer's flag has reached the step it is about to read.
 struct PeerExchange {
     double2            *peer_next[kMaxPeers];    // pos_next of every rank, as mapped here
     unsigned long long *peer_flags[kMaxPeers];   // flag array of every rank, as mapped here
@@ -265,8 +266,8 @@ __device__ __forceinline__ double half_drift(double x, double v, double dt)
 //   r2^(-3/2) = y0^3 * (1-e)^(-3/2) = y0^3 * (1 + e*(3/2 + 15/8 e) + O(e^3)),
 //   |e| < 2^-19 so the dropped term is < 2^-56.
 // r2 == 0 (an exactly coincident pair, :1199-1201) or a non-finite r2 yields a
-// NaN that poisons the sum; the commit kernel detects it and redoes that body
-// on the guarded path, which keeps the test out of this loop.
+// NaN that poisons the sum; commit_iblock detects it and redoes that body on
+// the guarded path, which keeps the test out of this loop.
 __device__ __forceinline__ double pair_weight(double dx, double dy, double mj)
 {
     const double r2 = fma(dy, dy, dx * dx);
