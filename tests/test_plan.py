@@ -70,3 +70,17 @@ def test_shape_follows_problem_size():
     assert (forced["threads"], forced["bodies_per_thread"], forced["ctas_per_sm"]) == (256, 2, 2)
     with pytest.raises(g.GravityError):
         g.plan_probe(0)
+
+
+def test_plan_of_a_very_large_system_is_cheap_and_exact():
+    # 2^26 bodies on 8 GPUs: 1.7e10 work units; the plan is O(CTAs + i-blocks)
+    n = 1 << 26
+    info, segs = g.plan_probe(n, nranks=8, rank=6)
+    assert info["n_tile"] == n // 256 and info["n_iblock"] == n // 8 // 1024 and info["n_cta"] == 148
+    per_cta = np.zeros(148, dtype=np.int64)
+    units = 0
+    for cta, iblock, t0, t1, row in segs:
+        per_cta[cta] += t1 - t0
+        units += t1 - t0
+    assert units == info["n_iblock"] * info["n_tile"]
+    assert per_cta.max() - per_cta.min() <= 1
