@@ -79,8 +79,8 @@ def test_plan_of_a_very_large_system_is_cheap_and_exact():
     assert info["n_tile"] == n // 256 and info["n_iblock"] == n // 8 // 1024 and info["n_cta"] == 148
     per_cta = np.zeros(148, dtype=np.int64)
     units = 0
-    for cta, iblock, t0, t1, row in segs:
+    for cta, iblock, t0, t1, row in segs.tolist():      # python ints: 2^31 units overflow int32
         per_cta[cta] += t1 - t0
         units += t1 - t0
-    assert units == info["n_iblock"] * info["n_tile"]
+    assert units == info["n_iblock"] * info["n_tile"] == 1 << 31
     assert per_cta.max() - per_cta.min() <= 1
