@@ -28,8 +28,13 @@ $(PKG)/gravity_headless: $(PKG)/host/gravity_headless.c $(PKG)/libgravity_host.s
 oracle:
 	$(MAKE) -C oracle
 
+tools: tools/fp64_microbench tools/fp64_mix
+
+tools/%: tools/%.cu
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -o $@ $<
+
 clean:
 	rm -f $(PKG)/*.so $(PKG)/gravity_headless
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle tools clean
