@@ -47,6 +47,30 @@ NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, 1): 48045824 + 33719040}
 DT = 1
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line.  Native libraries print there too
+    (NCCL announces its version on stdout when a communicator is created), so
+    file descriptor 1 is pointed at stderr for the rest of the run and the real
+    stdout is kept aside for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(record):
+    data = (json.dumps(record) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -111,6 +135,7 @@ def run_reference(args, rank):
     times the oracle port, which tests/ prove bit-identical to it."""
     if rank != 0:
         return
+    claim_stdout()
     import proj_entropy_b200 as g
     n = args.bodies
     nthreads, ncpu = host_threads()
@@ -136,7 +161,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -199,6 +224,7 @@ def measured_peaks():
 
 
 def run_ours(args, rank, world, local_rank):
+    claim_stdout()
     import numpy as np
     import torch
     import proj_entropy_b200 as g
@@ -361,7 +387,7 @@ def run_ours(args, rank, world, local_rank):
             line["equal_mass_path"] = extra
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     sampler.stop()
     h.close()
     ranks.close()
