@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <vector>
 
@@ -116,6 +117,22 @@ int fail(gravity_cuda_t *h, const char *fmt, ...)
         if (r_ != ncclSuccess)                                                                \
             return fail((h), "NCCL %s: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
+
+// No C++ exception may cross the C ABI: host-side allocations (std::vector,
+// new) that fail become an ordinary error return.
+template <class F>
+int no_throw(gravity_cuda_t *h, F &&body) noexcept
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return fail(h, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(h, "host error: %s", e.what());
+    } catch (...) {
+        return fail(h, "unknown host error");
+    }
+}
 
 int check_device(gravity_cuda_t *h, int device)
 {
@@ -326,7 +343,7 @@ void make_plan(int64_t n, int64_t n_local, int64_t i0, int64_t chunk, int nranks
     for (int b = 0; b < out.n_iblock; ++b) out.ib_begin[b + 1] += out.ib_begin[b];
 }
 
-int build_plan(gravity_cuda_t *h)
+int build_plan_impl(gravity_cuda_t *h)
 {
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
@@ -373,6 +390,11 @@ int build_plan(gravity_cuda_t *h)
     return 0;
 }
 
+int build_plan(gravity_cuda_t *h)
+{
+    return no_throw(h, [&] { return build_plan_impl(h); });
+}
+
 // ---- timing helpers -------------------------------------------------------------
 
 void hot_event(gravity_cuda_t *h, DeviceCtx &c)
@@ -382,7 +404,12 @@ void hot_event(gravity_cuda_t *h, DeviceCtx &c)
     if (c.kev_used == c.kev.size()) {
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return;
-        c.kev.push_back(e);
+        try {
+            c.kev.push_back(e);
+        } catch (...) {
+            cudaEventDestroy(e);
+            return;
+        }
     }
     cudaEventRecord(c.kev[c.kev_used++], c.stream);
 }
@@ -700,14 +727,14 @@ static int create_common(gravity_cuda_t **out, int64_t n, int nranks, bool singl
 
 int gravity_cuda_create(gravity_cuda_t **out, int64_t n, int ngpus)
 {
-    return create_common(out, n, ngpus, true, 0, 0, nullptr, 0);
+    return no_throw(nullptr, [&] { return create_common(out, n, ngpus, true, 0, 0, nullptr, 0); });
 }
 
 int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nranks, int device,
                              const void *nccl_id, size_t id_bytes)
 {
     if (rank < 0 || rank >= nranks) return fail(nullptr, "rank %d out of range 0..%d", rank, nranks - 1);
-    return create_common(out, n, nranks, false, rank, device, nccl_id, id_bytes);
+    return no_throw(nullptr, [&] { return create_common(out, n, nranks, false, rank, device, nccl_id, id_bytes); });
 }
 
 void gravity_cuda_destroy(gravity_cuda_t *h)
@@ -1035,6 +1062,7 @@ int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size
     if (!objects) return fail(h, "step_objects: NULL objects");
     if (n != h->n) return fail(h, "step_objects: n=%lld but the handle was created for %lld", (long long)n,
                                (long long)h->n);
+    return no_throw(h, [&]() -> int {
     std::vector<double> soa((size_t)5 * n);
     double *m = soa.data(), *x = m + n, *y = x + n, *vx = y + n, *vy = vx + n;
     for (int64_t i = 0; i < n; ++i) {
@@ -1057,9 +1085,10 @@ int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size
         memcpy(o + off_vy, &vy[i], sizeof(double));
     }
     return 0;
+    });
 }
 
-int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential)
+static int energy_impl(gravity_cuda_t *h, double *kinetic, double *potential)
 {
     if (!h) return fail(nullptr, "energy: NULL handle");
     if (!h->uploaded) return fail(h, "energy before upload");
@@ -1109,6 +1138,11 @@ int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential)
     if (kinetic) *kinetic = (double)ke;
     if (potential) *potential = (double)(-0.5L * (long double)kG * pe);   // each pair was counted twice
     return 0;
+}
+
+int gravity_cuda_energy(gravity_cuda_t *h, double *kinetic, double *potential)
+{
+    return no_throw(h, [&] { return energy_impl(h, kinetic, potential); });
 }
 
 int gravity_cuda_timer_start(gravity_cuda_t *h)
@@ -1179,8 +1213,8 @@ int gravity_cuda_kernel_times(gravity_cuda_t *h, double *ms_out, int64_t cap, in
     return 0;
 }
 
-int gravity_cuda_plan_probe(int64_t n, int nranks, int rank, int num_sms, int threads, int bpt, int ctas_per_sm,
-                            int32_t *info, int32_t *seg_out, int64_t seg_cap)
+static int plan_probe_impl(int64_t n, int nranks, int rank, int num_sms, int threads, int bpt, int ctas_per_sm,
+                           int32_t *info, int32_t *seg_out, int64_t seg_cap)
 {
     if (n < 1 || nranks < 1 || rank < 0 || rank >= nranks || num_sms < 1 || !info)
         return fail(nullptr, "plan_probe: bad argument");
@@ -1207,6 +1241,14 @@ int gravity_cuda_plan_probe(int64_t n, int nranks, int rank, int num_sms, int th
         }
     }
     return 0;
+}
+
+int gravity_cuda_plan_probe(int64_t n, int nranks, int rank, int num_sms, int threads, int bpt, int ctas_per_sm,
+                            int32_t *info, int32_t *seg_out, int64_t seg_cap)
+{
+    return no_throw(nullptr, [&] {
+        return plan_probe_impl(n, nranks, rank, num_sms, threads, bpt, ctas_per_sm, info, seg_out, seg_cap);
+    });
 }
 
 int gravity_cuda_launch_count(const gravity_cuda_t *h, int64_t *launches)
