@@ -182,7 +182,11 @@ int gravity_scenario_load_ex(const char *pathname, int32_t inherit_dt, double in
             } else if ((strcmp(pname, "DT_LINUX") == 0 || strcmp(pname, "DT_ANDROID") == 0) &&
                        strcmp(punits, "SEC") == 0) {
                 if (strcmp(pname, "DT_ANDROID") == 0) continue;   /* other platform's line */
-                new_dt = (int32_t)pvalue;                     /* truncation, :320 */
+                /* truncation, :320.  Out-of-range and NaN values are undefined in C;
+                 * the reference's x86-64 build yields INT32_MIN for them
+                 * (cvttsd2si), which then snaps to the table floor: do the same,
+                 * explicitly. */
+                new_dt = (pvalue > -2147483649.0 && pvalue < 2147483648.0) ? (int32_t)pvalue : INT32_MIN;
                 for (i = N_VALID_DT - 1; i >= 0; i--) {
                     if (new_dt >= k_valid_dt[i]) {
                         new_dt = k_valid_dt[i];

@@ -111,3 +111,12 @@ def test_snapshot_round_trip(tmp_path):
     bad.write_bytes(b"NOTASNAP" + bytes(64))
     with pytest.raises(OSError):
         g.snapshot_read(str(bad))
+
+
+def test_out_of_range_dt_behaves_like_the_reference_build(tmp_path):
+    # (int32_t)1e300 and (int32_t)NaN are undefined in C; the reference's x86-64
+    # build produces INT32_MIN, which snaps to the table floor of 1 second
+    for text in ("1e300", "nan", "-1e12", "4e9"):
+        p = tmp_path / "dt"
+        p.write_text("PARAM DT_LINUX %s SEC\na 0 0 0 0 1E30 1 RED 5\n" % text)
+        assert g.load_scenario(str(p)).dt == 1, text
