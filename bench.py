@@ -121,6 +121,12 @@ def cpu_sample(state, rows, nthreads):
     return rows * (n - 1) / dt, dt
 
 
+def all_cores_sample(state, rows, ncpu):
+    """For information: the same loop on every host cpu."""
+    rate, secs = cpu_sample(state, max(ncpu, rows // 2), ncpu)
+    return {"value": rate, "cores": ncpu, "seconds": secs}
+
+
 def auto_rows(n, nthreads, target_cpu_seconds=20.0):
     # ~2e8 pairs/s/thread on current Xeons (BASELINE.md section 2)
     rows = int(target_cpu_seconds * 2.0e8 / max(1, n - 1))
@@ -149,6 +155,7 @@ def run_reference(args, rank):
         t_total += secs
         pairs += rows * (n - 1)
     value = pairs / t_total
+    all_cores = all_cores_sample(state, rows, ncpu) if ncpu != nthreads else None
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n * (n - 1) / value,
@@ -157,7 +164,8 @@ def run_reference(args, rank):
                    "step": "row-subsampled: %d i-rows x all %d j-bodies per timed step" % (rows, n)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
                          "sample": "%d rows x %d bodies per step, %d steps; host has %d cpus; thread count is the "
-                                   "reference's policy min(nproc-1,16)" % (rows, n, args.steps, ncpu)},
+                                   "reference's policy min(nproc-1,16)" % (rows, n, args.steps, ncpu),
+                         "all_cores": all_cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -346,7 +354,8 @@ def run_ours(args, rank, world, local_rank):
         rate, secs = cpu_sample(state, rows, nthreads)
         cpu = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
                "sample": "%d i-rows x all %d j-bodies (%.1f s wall on %d of %d host cpus); oracle port, bit-identical "
-                         "to the unmodified reference TU" % (rows, n, secs, nthreads, ncpu)}
+                         "to the unmodified reference TU" % (rows, n, secs, nthreads, ncpu),
+               "all_cores": all_cores_sample(state, rows, ncpu) if ncpu != nthreads else None}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -378,7 +387,9 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry: "
                                         "keys %s)" % sorted(peaks.keys())[:4],
                          "peak_sm_mhz": fp64_mhz, "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
-                         "flops_per_pair": FLOPS_PER_PAIR, "kernel": "k_tiled_accumulate",
+                         "flops_per_pair": FLOPS_PER_PAIR, "reference_fp64_ops_per_pair": 13,
+                         "sass_fp64_instr_per_pair": 12 if args.mass_fold else 13, "sass_mufu_per_pair": 1,
+                         "kernel": "k_tiled_accumulate",
                          "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kernel_launches,
                          "kernel_share_of_step": kernel_ms / ms if ms else None,
                          "job_frac_of_nominal": FLOPS_PER_PAIR * value / 1e12 / (FP64_NOMINAL_TFLOPS * world)},
