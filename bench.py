@@ -127,6 +127,30 @@ def all_cores_sample(state, rows, ncpu):
     return {"value": rate, "cores": ncpu, "seconds": secs}
 
 
+def reference_tu_sample(steps=200000):
+    """For information: the UNMODIFIED reference translation unit (oracle/_ref,
+    built from /root/reference by oracle/Makefile) at a scale it can represent --
+    the authored 15-body scenario, 15 worker threads + the metering participant,
+    two spin barriers per step (sim_gravity.c:1140, :1226).  Not the bench
+    workload (MAX_OBJECT = 200): it shows the regime the reference really runs in."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gravity")
+    scen = os.path.join(ROOT, "tests", "golden", "scenarios", "random15")
+    if not (os.path.exists(exe) and os.path.exists(scen)):
+        return None
+    try:
+        t0 = time.perf_counter()
+        subprocess.run([exe, scen, "0"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=60, check=True)
+        t1 = time.perf_counter()
+        subprocess.run([exe, scen, "0", str(steps)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300,
+                       check=True)
+        t2 = time.perf_counter()
+    except Exception:
+        return None
+    secs = max(1e-6, (t2 - t1) - (t1 - t0) - 0.05)      # minus start-up and the extra 50 ms STOP round of the second dump
+    return {"bodies": 15, "steps": steps, "seconds": secs, "value": 15 * 14 * steps / secs, "unit": UNIT,
+            "threads": 16, "what": "unmodified sim_gravity.c through oracle/_ref/ref_gravity"}
+
+
 def auto_rows(n, nthreads, target_cpu_seconds=20.0):
     # ~2e8 pairs/s/thread on current Xeons (BASELINE.md section 2)
     rows = int(target_cpu_seconds * 2.0e8 / max(1, n - 1))
@@ -165,7 +189,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
                          "sample": "%d rows x %d bodies per step, %d steps; host has %d cpus; thread count is the "
                                    "reference's policy min(nproc-1,16)" % (rows, n, args.steps, ncpu),
-                         "all_cores": all_cores},
+                         "all_cores": all_cores, "reference_tu_small": reference_tu_sample()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
