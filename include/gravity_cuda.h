@@ -60,10 +60,11 @@ typedef struct gravity_cuda gravity_cuda_t;
 
 /* ---- life cycle --------------------------------------------------------- */
 
-/* Single-process handle over devices 0..ngpus-1 of one box (ngpus >= 1).
- * Replaces worker creation at sim_gravity.c:425-442: the i-bodies that the
- * reference strides over max_thread pthreads (:1183) are sharded in
- * contiguous blocks over the GPUs. */
+/* Single-process handle over devices 0..ngpus-1 of one box, 1 <= ngpus <= 8
+ * (the GPUs of one NVSwitch box; typically 1, 2, 4 or 8).  Replaces worker
+ * creation at sim_gravity.c:425-442: the i-bodies that the reference strides
+ * over max_thread pthreads (:1183) are sharded in contiguous blocks over the
+ * GPUs. */
 int gravity_cuda_create(gravity_cuda_t **out, int64_t n, int ngpus);
 
 /* One-process-per-GPU handle (torchrun style): this process is `rank` of
@@ -87,7 +88,11 @@ int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nran
 int gravity_cuda_p2p_export(gravity_cuda_t *h, void *blob, size_t bytes);
 int gravity_cuda_p2p_connect(gravity_cuda_t *h, const void *blobs_all_ranks, size_t bytes);
 
-/* Replaces sim_gravity_terminate's worker join (sim_gravity.c:487-502). */
+/* Replaces sim_gravity_terminate's worker join (sim_gravity.c:487-502).  Waits
+ * for the handle's own work and, with the peer-memory exchange, until every peer
+ * has published the handle's current step (a peer's last step kernel stores into
+ * this device's buffers until then) before anything is freed.  In rank mode it is
+ * therefore collective like step: call it on every rank after the same steps. */
 void gravity_cuda_destroy(gravity_cuda_t *h);
 
 /* Message of the last failure on this handle; h == NULL returns the message of
@@ -98,21 +103,43 @@ const char *gravity_cuda_last_error(const gravity_cuda_t *h);
  * kernel: 128|256), "bodies_per_thread" (1|2|4), "ctas_per_sm" (1..8) -- 0, the
  * default, lets the library pick the shape that fills the SMs best for N,
  * "exchange" (0: NCCL all-gather of the new positions, default; 1: peer-memory
- * stores + flags, see gravity_cuda_p2p_connect),
+ * stores + flags, see gravity_cuda_p2p_connect; collective in rank mode),
  * "mass_fold" (0|1, default 1: j-tiles whose 256 masses are bit-identical are
  * summed without the mass and scaled once per tile -- 12 instead of 13 FP64
- * instructions per pair; results differ from mass_fold=0 by rounding only).
- * Must be set before the first step/accel after create. */
+ * instructions per pair; results differ from mass_fold=0 by rounding only),
+ * "persistent" (0|1, default 1: all nsteps of a step call run in ONE launch of
+ * the tiled kernel, the steps chained by per-i-block ready counters instead of
+ * kernel boundaries; used on one GPU and with exchange=1; 0 = one launch per
+ * step, which the NCCL exchange always uses),
+ * "download_scope" (0: download/accel/path_read return all bodies on every rank,
+ * default; 1: in rank mode only the caller's own shard [i0, i0+n_local) of the
+ * output arrays is written -- no gather, 32*N/P bytes per rank),
+ * "spin_timeout_ms" (default 10000; 0 = wait for ever): how long a kernel waits
+ * for a peer's step flag or for an i-block of its own device before it gives up.
+ * A wait that gives up sets a device flag that stops every kernel of the handle
+ * from storing or publishing anything further; the state is then partly advanced
+ * and the handle is FAIL-STOP: sync/step/download report the timeout and every
+ * later call fails.  Raise the limit when a rank may legitimately stall longer
+ * between two collective calls.
+ * "trace" (0|1): record per-CTA time stamps of the tiled kernel (gravity_cuda_trace_read).
+ * Shape options must be set before the first step/accel after create. */
 int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value);
 
 /* ---- state -------------------------------------------------------------- */
 
 /* Host SoA, n doubles each: MASS, X, Y, VX, VY of object_t
- * (sim_gravity.c:85-90).  In rank mode every rank passes the full arrays. */
+ * (sim_gravity.c:85-90).  Every device copies only its own shard from the host
+ * and the devices complete each other over NVLink (one all-gather), so 40*N
+ * bytes cross PCIe in total whatever the number of GPUs.  In rank mode every
+ * rank passes full-length arrays holding the same values; only the entries of
+ * its own shard are read.  `mass` may be NULL after the first upload: the masses
+ * stay as they are (they never change during a run, sim_gravity.c:1193).
+ * Returns as soon as the host arrays have been consumed. */
 int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x,
                         const double *y, const double *vx, const double *vy);
 
-/* Any pointer may be NULL.  Full-length arrays are returned on every rank. */
+/* Any pointer may be NULL.  Full-length arrays are returned on every rank unless
+ * "download_scope" = 1. */
 int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, double *vy);
 
 /* ---- the hot path ------------------------------------------------------- */
@@ -126,6 +153,23 @@ int gravity_cuda_step(gravity_cuda_t *h, int32_t dt, int64_t nsteps);
 /* Same, but only enqueues the work; gravity_cuda_sync() waits for it. */
 int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps);
 int gravity_cuda_sync(gravity_cuda_t *h);
+
+/* PATH ring on the device.  The reference's commit block appends every body's
+ * new position to its PATH ring once per simulated day (sim_gravity.c:1230-1260:
+ * `day = sim_time/86400` taken BEFORE `sim_time += DT`, a sample when it differs
+ * from the function-static last_day).  path_enable() allocates a ring of
+ * `capacity` rows of n positions per device (0 frees it) and resets the sample
+ * count; step_path() runs nsteps like gravity_cuda_step() and lets the step
+ * kernels themselves take the samples -- also inside the kernels that run a whole
+ * batch in one launch -- so a run at DT = 1 day needs no host round trip per step.
+ * The caller passes sim_time before the batch and last_day (in/out) and advances
+ * sim_time by dt*nsteps itself; *path_tail receives the samples taken since
+ * path_enable.  path_read() returns samples first..first+count-1 sample-major
+ * (x[k*n + i]); only the last `capacity` samples are available. */
+int gravity_cuda_path_enable(gravity_cuda_t *h, int64_t capacity);
+int gravity_cuda_step_path(gravity_cuda_t *h, int32_t dt, int64_t nsteps, int64_t sim_time,
+                           int32_t *last_day, int64_t *path_tail);
+int gravity_cuda_path_read(gravity_cuda_t *h, int64_t first, int64_t count, double *x, double *y);
 
 /* AX, AY exactly as at sim_gravity.c:1207-1208 for the current state (n
  * doubles each); the state is not advanced. */
@@ -163,6 +207,13 @@ int gravity_cuda_kernel_time(gravity_cuda_t *h, double *ms_total, int64_t *launc
 /* The individual launch durations behind gravity_cuda_kernel_time (ms, in launch
  * order, at most `cap` of them); *count receives how many were recorded. */
 int gravity_cuda_kernel_times(gravity_cuda_t *h, double *ms_out, int64_t cap, int64_t *count);
+
+/* Developer aid (option "trace" = 1): per-CTA globaltimer stamps (ns) of the last
+ * tiled launch on the handle's first device, GRAVITY_CUDA_TRACE_EVENTS per CTA:
+ * [0] CTA start, [1] first j-tile in shared memory, [2] tiles of the first step
+ * done, [3] commit duty of the first step done, [4] CTA end. */
+#define GRAVITY_CUDA_TRACE_EVENTS 8
+int gravity_cuda_trace_read(gravity_cuda_t *h, uint64_t *stamps, int64_t cap_ctas, int64_t *n_cta);
 
 /* Dependent-free DFMA microbenchmark on `device`: measured FP64 FMA-pipe
  * throughput in TFLOP/s (2 flops per lane-FMA) and the SM clock it ran at

@@ -57,8 +57,24 @@ void gravity_scenario_free(gravity_scenario_t *s);
 
 /* Writes the state back out in the reference's file format (absolute
  * coordinates, no indentation), the inverse of the reader; the reference's
- * ENABLE_LOGGING dump (sim_gravity.c:444-467) is the nearest equivalent. */
+ * ENABLE_LOGGING dump (sim_gravity.c:444-467) is the nearest equivalent.
+ * The file is written so that the REFERENCE's own parser (sim_gravity.c:272-402)
+ * rebuilds the same bits: names are made single tokens (empty -> B<index>, white
+ * space -> '_', no leading '#', not the word PARAM; :277-289, :341-349),
+ * SIM_WIDTH is written as the snapping table's own literal (:299-311), the DT
+ * lines are left out when dt == 0 ("inherit", :222-223), and states the format
+ * cannot carry are refused instead of being altered silently:
+ *   GRAVITY_SAVE_E_TOO_MANY  n > 200, the reference stops reading there (:398-401)
+ *   GRAVITY_SAVE_E_DT        dt is not in valid_dt[] and would be snapped (:320-329)
+ *   GRAVITY_SAVE_E_VALUE     a non-finite body field
+ * One thing the format itself loses: -0.0 reloads as +0.0 (X + relto[0].X, :380). */
+#define GRAVITY_SAVE_E_IO        (-1)
+#define GRAVITY_SAVE_E_TOO_MANY  (-2)
+#define GRAVITY_SAVE_E_DT        (-3)
+#define GRAVITY_SAVE_E_VALUE     (-4)
+#define GRAVITY_SAVE_E_ARG       (-5)
 int gravity_scenario_save(const gravity_scenario_t *s, const char *pathname);
+const char *gravity_scenario_save_error(int code);
 
 /* Planar projection of a Plummer model (Aarseth, Henon & Wielen 1974
  * sampling), SI units: total mass 1.989E30 kg split equally, scale radius

@@ -43,16 +43,21 @@ struct DeviceCtx {
     // peer-memory exchange
     unsigned long long *flags = nullptr;           // [kMaxPeers], written by the peers
     unsigned int       *commit_counter = nullptr;
-    unsigned int       *status = nullptr;
+    unsigned int       *status = nullptr;          // kStatus*: != 0 makes the handle fail-stop
     double2            *peer_pos[2][kMaxPeers] = {};
     unsigned long long *peer_flags[kMaxPeers] = {};
     bool                ipc_opened[kMaxPeers] = {};
-    double  *stage = nullptr;      // 4 x npad doubles: SoA staging for upload / download
+    double  *stage = nullptr;      // 5 x npad doubles: SoA staging for upload / download
     double  *kin = nullptr, *pot = nullptr;
-    double2 *partial = nullptr;
+    double2 *partial_hi = nullptr, *partial_lo = nullptr;
     Segment *seg = nullptr;
     int32_t *cta_seg_begin = nullptr;
     int32_t *iblock_seg_begin = nullptr;
+    unsigned long long *counters = nullptr;        // arrivals | slices_done | iblock_ready | iblocks_done
+    unsigned long long *trace = nullptr;           // [n_cta][kTraceEvents], option "trace"
+    double2 *ring = nullptr;                       // PATH ring [path_capacity][npad]
+    cudaEvent_t ev_copy = nullptr;                 // host buffers of upload() consumed
+    long long clock_khz = 0;
 
     int64_t i0 = 0;          // global index of local body 0
     int64_t n_local = 0;     // real bodies in this shard
@@ -62,8 +67,6 @@ struct DeviceCtx {
     Phase phase[1];
     int n_iblock = 0;
     int local_tile_begin = 0, local_tile_end = 0;   // j-tiles of this rank's own shard
-    int32_t *iblock_arrivals = nullptr;             // [n_iblock], see k_tiled_accumulate
-    int32_t *iblocks_done = nullptr;
     int n_seg = 0;
     int threads = 0, bpt = 0, minb = 0;
 
@@ -85,8 +88,18 @@ struct gravity_cuda {
     int opt_threads = 0, opt_bpt = 0, opt_ctas_per_sm = 0;   // 0: chosen per problem size (build_plan)
     int opt_mass_fold = 1;
     int opt_exchange = 0;            // 0: NCCL all-gather, 1: peer-memory stores + flags
+    int opt_persistent = 1;          // 1: all steps of a batch in one launch where the exchange allows it
+    int opt_trace = 0;
+    int opt_download_scope = 0;      // 0: full arrays on every rank, 1: only the caller's own shard
+    int opt_debug_shard_of = 0;      // developer aid: plan and run like rank 0 of this many ranks, without peers
+    int64_t opt_spin_timeout_ms = 10000;
     bool p2p_connected = false;
-    unsigned long long step_id = 0;  // commits published so far (peer-memory exchange)
+    bool mass_uploaded = false;
+    bool dead = false;               // a device-side wait gave up: fail-stop
+    unsigned long long step_id = 0;  // steps committed since create (absolute step number of the state)
+    unsigned long long epoch = 0;    // evaluations done with the current plan of the tiled kernel
+    int64_t path_capacity = 0;       // rows of the PATH ring (0: off)
+    int64_t path_tail = 0;           // samples taken since path_enable
     int64_t launches = 0;
     bool timing = false;
     char err[200] = "";
@@ -158,16 +171,16 @@ int effective_kernel(const gravity_cuda_t *h)
 
 // ---- kernel dispatch over (threads, bodies per thread) ----------------------
 
-typedef void (*accum_kernel_t)(const AccumParams);
+typedef void (*accum_kernel_t)(const TiledParams);
 
 template <int T, int R>
 accum_kernel_t accum_for_minb(int minb)
 {
     switch (minb) {
-    case 1: return k_tiled_accumulate<T, R, 1>;
-    case 2: return k_tiled_accumulate<T, R, 2>;
-    case 3: return k_tiled_accumulate<T, R, 3>;
-    default: return k_tiled_accumulate<T, R, 4>;
+    case 1: return k_tiled_steps<T, R, 1>;
+    case 2: return k_tiled_steps<T, R, 2>;
+    case 3: return k_tiled_steps<T, R, 3>;
+    default: return k_tiled_steps<T, R, 4>;
     }
 }
 
@@ -356,7 +369,13 @@ int build_plan_impl(gravity_cuda_t *h)
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe, threads, 0));
         if (occ < 1) return fail(h, "tiled kernel does not fit on an SM");
         HostPlan plan;
-        make_plan(h->n, c.n_local, c.i0, h->chunk, h->nranks, c.num_sms, threads, bpt, std::min(occ, ctas), plan);
+        if (h->opt_debug_shard_of > 1) {
+            const int64_t per = (h->n + h->opt_debug_shard_of - 1) / h->opt_debug_shard_of;
+            const int64_t chunk = std::max<int64_t>(kTile, ((per + kTile - 1) / kTile) * kTile);
+            make_plan(h->n, c.n_local, 0, chunk, h->opt_debug_shard_of, c.num_sms, threads, bpt, std::min(occ, ctas), plan);
+        } else {
+            make_plan(h->n, c.n_local, c.i0, h->chunk, h->nranks, c.num_sms, threads, bpt, std::min(occ, ctas), plan);
+        }
         c.threads = plan.threads;
         c.bpt = plan.bpt;
         c.minb = plan.ctas;
@@ -368,24 +387,33 @@ int build_plan_impl(gravity_cuda_t *h)
         c.n_seg = (int)plan.segs.size();
         const int IB = c.threads * c.bpt;
 
-        cudaFree(c.seg); cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin); cudaFree(c.partial);
-        cudaFree(c.iblock_arrivals); cudaFree(c.iblocks_done);
-        c.seg = nullptr; c.cta_seg_begin = nullptr; c.iblock_seg_begin = nullptr; c.partial = nullptr;
-        c.iblock_arrivals = nullptr; c.iblocks_done = nullptr;
-        CUDA_TRY(h, cudaMalloc(&c.iblock_arrivals, sizeof(int32_t) * std::max(1, c.n_iblock)));
-        CUDA_TRY(h, cudaMalloc(&c.iblocks_done, sizeof(int32_t)));
-        CUDA_TRY(h, cudaMemset(c.iblock_arrivals, 0, sizeof(int32_t) * std::max(1, c.n_iblock)));
-        CUDA_TRY(h, cudaMemset(c.iblocks_done, 0, sizeof(int32_t)));
+        cudaFree(c.seg); cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin); cudaFree(c.partial_hi);
+        cudaFree(c.partial_lo); cudaFree(c.counters); cudaFree(c.trace);
+        c.seg = nullptr; c.cta_seg_begin = nullptr; c.iblock_seg_begin = nullptr; c.partial_hi = nullptr;
+        c.partial_lo = nullptr; c.counters = nullptr; c.trace = nullptr;
+        // arrivals[n_iblock] | slices_done[n_iblock] | iblock_ready[n_iblock] | iblocks_done[1]: monotonic,
+        // zeroed here together with h->epoch (iblock_ready compares against absolute step numbers and
+        // is only consulted for steps after the first of a launch, so 0 is a valid start)
+        const size_t n_counters = (size_t)3 * std::max(1, c.n_iblock) + 1;
+        CUDA_TRY(h, cudaMalloc(&c.counters, sizeof(unsigned long long) * n_counters));
+        CUDA_TRY(h, cudaMemset(c.counters, 0, sizeof(unsigned long long) * n_counters));
+        if (h->opt_trace) {
+            const size_t n_trace = (size_t)std::max(1, plan.n_cta) * kTraceEvents;
+            CUDA_TRY(h, cudaMalloc(&c.trace, sizeof(unsigned long long) * n_trace));
+            CUDA_TRY(h, cudaMemset(c.trace, 0, sizeof(unsigned long long) * n_trace));
+        }
         CUDA_TRY(h, cudaMalloc(&c.seg, sizeof(Segment) * std::max<size_t>(1, plan.segs.size())));
         CUDA_TRY(h, cudaMalloc(&c.cta_seg_begin, sizeof(int32_t) * std::max<size_t>(1, plan.cta_begin.size())));
         CUDA_TRY(h, cudaMalloc(&c.iblock_seg_begin, sizeof(int32_t) * plan.ib_begin.size()));
-        CUDA_TRY(h, cudaMalloc(&c.partial, sizeof(double2) * std::max<size_t>(1, plan.segs.size()) * IB));
+        CUDA_TRY(h, cudaMalloc(&c.partial_hi, sizeof(double2) * std::max<size_t>(1, plan.segs.size()) * IB));
+        CUDA_TRY(h, cudaMalloc(&c.partial_lo, sizeof(double2) * std::max<size_t>(1, plan.segs.size()) * IB));
         CUDA_TRY(h, cudaMemcpy(c.seg, plan.segs.data(), sizeof(Segment) * plan.segs.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(h, cudaMemcpy(c.cta_seg_begin, plan.cta_begin.data(), sizeof(int32_t) * plan.cta_begin.size(),
                                cudaMemcpyHostToDevice));
         CUDA_TRY(h, cudaMemcpy(c.iblock_seg_begin, plan.ib_begin.data(), sizeof(int32_t) * plan.ib_begin.size(),
                                cudaMemcpyHostToDevice));
     }
+    h->epoch = 0;
     h->planned = true;
     return 0;
 }
@@ -414,150 +442,224 @@ void hot_event(gravity_cuda_t *h, DeviceCtx &c)
     cudaEventRecord(c.kev[c.kev_used++], c.stream);
 }
 
-// ---- one step on every local device -----------------------------------------------
+// ---- steps on every local device ----------------------------------------------------
 
-CommitParams commit_params(gravity_cuda_t *h, DeviceCtx &c, double dt, bool export_accel)
+bool p2p_active(const gravity_cuda_t *h) { return h->opt_exchange == 1 && h->nranks > 1; }
+
+WaitPolicy wait_policy(const gravity_cuda_t *h, const DeviceCtx &c)
+{
+    WaitPolicy wp;
+    wp.status = c.status;
+    wp.timeout_cycles = h->opt_spin_timeout_ms > 0 ? (long long)h->opt_spin_timeout_ms * c.clock_khz : 0;
+    return wp;
+}
+
+PeerExchange peer_exchange(const gravity_cuda_t *h, const DeviceCtx &c, bool enabled)
+{
+    PeerExchange X;
+    memset(&X, 0, sizeof(X));
+    X.enabled = enabled ? 1 : 0;
+    X.rank = c.rank;
+    X.nranks = h->nranks;
+    X.flags = c.flags;
+    for (int r = 0; r < h->nranks && r < kMaxPeers; ++r) {
+        X.peer_pos[0][r] = c.peer_pos[0][r];
+        X.peer_pos[1][r] = c.peer_pos[1][r];
+        X.peer_flags[r] = c.peer_flags[r];
+    }
+    return X;
+}
+
+// The commit block's clock for a batch that starts at `sim_time` (sim_gravity.c:1232-1236).
+StepClock make_clock(const gravity_cuda_t *h, const DeviceCtx &c, int32_t dt, int64_t sim_time, int32_t last_day,
+                     bool sampling)
+{
+    StepClock k;
+    memset(&k, 0, sizeof(k));
+    k.dt = dt;
+    if (sampling && h->path_capacity > 0) {
+        k.day = sim_time / 86400;
+        k.rem = sim_time % 86400;
+        k.tail = h->path_tail;
+        k.capacity = h->path_capacity;
+        k.ring = c.ring;
+        k.npad = h->npad;
+        k.last_day = last_day;
+    }
+    return k;
+}
+
+CommitParams commit_params(gravity_cuda_t *h, DeviceCtx &c, double dt, bool export_accel, long long ring_row)
 {
     CommitParams P;
     memset(&P, 0, sizeof(P));
     P.pos_cur = c.pos[h->cur];
     P.pos_next = c.pos[h->cur ^ 1];
+    P.cur_next = h->cur ^ 1;
     P.vel = c.vel;
     P.mass = c.mass;
-    P.partial = c.partial;
-    P.iblock_seg_begin = c.iblock_seg_begin;
-    P.iblock_arrivals = c.iblock_arrivals;
-    P.iblocks_done = c.iblocks_done;
-    P.n_iblock = c.n_iblock;
     P.accel_out = c.accel;
+    P.ring_row = (ring_row >= 0 && c.ring) ? c.ring + (size_t)ring_row * h->npad : nullptr;
     P.n = h->n;
     P.i_global0 = c.i0;
     P.n_local = c.n_local;
-    P.iblock_size = c.threads * c.bpt;
     P.export_accel = export_accel ? 1 : 0;
     P.dt = dt;
-    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
-    P.wait_flags = p2p ? c.flags : nullptr;
+    P.commit_counter = c.commit_counter;
     P.wait_step = h->step_id;
-    P.px.enabled = (p2p && !export_accel) ? 1 : 0;
-    P.px.rank = c.rank;
-    P.px.nranks = h->nranks;
-    P.px.flags = c.flags;
-    P.px.commit_counter = c.commit_counter;
-    P.px.status = c.status;
-    P.px.step = h->step_id + 1;
-    for (int r = 0; r < h->nranks && r < kMaxPeers; ++r) {
-        P.px.peer_next[r] = c.peer_pos[h->cur ^ 1][r];
-        P.px.peer_flags[r] = c.peer_flags[r];
-    }
+    P.publish_step = h->step_id + 1;
+    P.wp = wait_policy(h, c);
+    P.px = peer_exchange(h, c, p2p_active(h));
     return P;
 }
 
-// The one launch of a tiled step: pairs, reduction, repair, kick + drift, hand-over.
-int launch_tiled(gravity_cuda_t *h, DeviceCtx &c, double dt, bool export_accel)
+// One cooperative launch of the tiled kernel: `nsteps` steps (pairs, reduction, repair,
+// kick + drift, hand-over, PATH samples), or one evaluation that only exports AX,AY.
+int launch_tiled(gravity_cuda_t *h, DeviceCtx &c, double dt, long long nsteps, bool export_accel, const StepClock &clk)
 {
     const DeviceCtx::Phase &ph = c.phase[0];
     if (ph.n_cta == 0) return 0;
-    AccumParams P;
+    TiledParams P;
     memset(&P, 0, sizeof(P));
-    P.pos = c.pos[h->cur];
+    P.pos[0] = c.pos[0];
+    P.pos[1] = c.pos[1];
+    P.cur = h->cur;
     P.mass = c.mass;
     P.vel = c.vel;
-    P.partial = c.partial;
+    P.accel_out = c.accel;
+    P.partial_hi = c.partial_hi;
+    P.partial_lo = c.partial_lo;
     P.seg = c.seg;
     P.cta_seg_begin = c.cta_seg_begin + ph.cta_seg_offset;
+    P.iblock_seg_begin = c.iblock_seg_begin;
     P.tile_mass = h->opt_mass_fold ? c.tile_mass : nullptr;
+    const size_t nb = (size_t)std::max(1, c.n_iblock);
+    P.arrivals = c.counters;
+    P.slices_done = c.counters + nb;
+    P.iblock_ready = c.counters + 2 * nb;
+    P.iblocks_done = c.counters + 3 * nb;
+    P.trace = c.trace;
+    P.epoch = h->epoch;
+    P.step_base = h->step_id;
+    P.nsteps = nsteps;
+    P.n = h->n;
     P.i_global0 = c.i0;
     P.n_local = c.n_local;
-    P.dt = dt;
-    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
-    P.wait_flags = p2p ? c.flags : nullptr;
-    P.wait_status = c.status;
-    P.wait_step = h->step_id;
-    P.wait_rank = c.rank;
-    P.wait_nranks = h->nranks;
+    P.n_iblock = c.n_iblock;
+    P.export_accel = export_accel ? 1 : 0;
     P.local_tile_begin = c.local_tile_begin;
     P.local_tile_end = c.local_tile_end;
-    P.cm = commit_params(h, c, dt, export_accel);
+    P.dt = dt;
+    P.clock = clk;
+    P.wp = wait_policy(h, c);
+    P.px = peer_exchange(h, c, p2p_active(h));
     accum_kernel_t k = pick_accum(c.threads, c.bpt, c.minb);
+    void *args[] = {&P};
     hot_event(h, c);
-    k<<<ph.n_cta, c.threads, 0, c.stream>>>(P);
+    // cooperative: every CTA is resident, which the in-kernel waits between CTAs rely on
+    CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)k, dim3(ph.n_cta), dim3(c.threads), args, 0, c.stream));
     hot_event(h, c);
     h->launches++;
-    CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
 
-// Evaluate sim_gravity.c:1183-1222 once on all local devices, either advancing
-// the state (export_accel == false) or writing AX,AY into ctx.accel.
-int enqueue_evaluation(gravity_cuda_t *h, double dt, bool export_accel, bool gather_after)
+// `nsteps` iterations of sim_gravity.c:1183-1222 + the commit (:1242-1245) on all local
+// devices, or (export_accel) one evaluation that writes AX,AY into ctx.accel and leaves
+// the state alone.  `clk0` carries sim_time/last_day for PATH sampling (capacity 0: off).
+int enqueue_steps(gravity_cuda_t *h, double dt, long long nsteps, bool export_accel, StepClock *clk0)
 {
+    if (h->dead) return fail(h, "the handle is dead: a device-side wait timed out earlier (see gravity_cuda.h)");
     const int kernel = effective_kernel(h);
     if (kernel == GRAVITY_CUDA_KERNEL_TILED && !h->planned) {
         if (build_plan(h) != 0) return -1;
     }
-    const bool p2p = h->opt_exchange == 1 && h->nranks > 1;
-    for (DeviceCtx &c : h->ctx) {
-        CUDA_TRY(h, cudaSetDevice(c.device));
-        if (c.n_local == 0) {
-            // an empty shard still has to tell its peers that it has nothing to send
-            if (p2p && !export_accel) {
-                const CommitParams P = commit_params(h, c, dt, false);
-                k_publish_only<<<1, 32, 0, c.stream>>>(P.px);
+    const bool p2p = p2p_active(h);
+    const bool gather = !export_accel && h->nranks > 1 && !p2p;          // NCCL all-gather after every step
+    // how many steps one launch may carry: the tiled kernel runs a whole batch unless an
+    // NCCL collective has to sit between the steps
+    const bool batched = kernel == GRAVITY_CUDA_KERNEL_TILED && !export_accel && !gather && h->opt_persistent;
+    StepClock host_clk;
+    memset(&host_clk, 0, sizeof(host_clk));
+    if (clk0) host_clk = *clk0;
+    long long done = 0;
+    while (done < nsteps) {
+        const long long chunk = batched ? nsteps - done : 1;
+        for (DeviceCtx &c : h->ctx) {
+            CUDA_TRY(h, cudaSetDevice(c.device));
+            StepClock dev_clk = host_clk;
+            dev_clk.ring = c.ring;
+            if (c.n_local == 0) {
+                // an empty shard still has to tell its peers that it has nothing to send
+                if (p2p && !export_accel) {
+                    k_publish_only<<<1, 32, 0, c.stream>>>(peer_exchange(h, c, true), h->step_id + (unsigned long long)chunk);
+                    h->launches++;
+                    CUDA_TRY(h, cudaGetLastError());
+                }
+                continue;
+            }
+            if (kernel == GRAVITY_CUDA_KERNEL_TILED) {
+                if (launch_tiled(h, c, dt, chunk, export_accel, dev_clk) != 0) return -1;
+            } else {
+                StepClock probe = host_clk;
+                const long long ring_row = export_accel ? -1 : clock_tick(probe);
+                const CommitParams P = commit_params(h, c, dt, export_accel, ring_row);
+                const int grid = (int)((c.n_local + kStrictThreads - 1) / kStrictThreads);
+                hot_event(h, c);
+                k_strict_rows<<<grid, kStrictThreads, 0, c.stream>>>(P);
+                hot_event(h, c);
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
             }
-            continue;
         }
-        if (kernel == GRAVITY_CUDA_KERNEL_TILED) {
-            if (launch_tiled(h, c, dt, export_accel) != 0) return -1;
-        } else {
-            const CommitParams P = commit_params(h, c, dt, export_accel);
-            const int grid = (int)((c.n_local + kStrictThreads - 1) / kStrictThreads);
-            hot_event(h, c);
-            k_strict_rows<<<grid, kStrictThreads, 0, c.stream>>>(P);
-            hot_event(h, c);
-            h->launches++;
-            CUDA_TRY(h, cudaGetLastError());
-        }
-    }
-    if (!export_accel && gather_after && h->nranks > 1) {
-        if (p2p) {
-            h->step_id++;      // the kernels stored into the peers and publish this step
-        } else {
-            // barrier B2 + the NEXT_* -> state copy (sim_gravity.c:1226, :1242-1245)
-            // become one in-place all-gather of the new positions.
-            NCCL_TRY(h, ncclGroupStart());
-            for (DeviceCtx &c : h->ctx) {
-                double2 *next = c.pos[h->cur ^ 1];
-                NCCL_TRY(h, ncclAllGather(next + c.i0, next, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
+        if (kernel == GRAVITY_CUDA_KERNEL_TILED) h->epoch += (unsigned long long)chunk;
+        if (!export_accel) {
+            for (long long k = 0; k < chunk; ++k) clock_tick(host_clk);
+            if (gather) {
+                // barrier B2 + the NEXT_* -> state copy (sim_gravity.c:1226, :1242-1245)
+                // become one in-place all-gather of the new positions.
+                NCCL_TRY(h, ncclGroupStart());
+                for (DeviceCtx &c : h->ctx) {
+                    double2 *next = c.pos[h->cur ^ 1];
+                    NCCL_TRY(h, ncclAllGather(next + c.i0, next, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
+                }
+                NCCL_TRY(h, ncclGroupEnd());
             }
-            NCCL_TRY(h, ncclGroupEnd());
+            h->step_id += (unsigned long long)chunk;
+            h->cur ^= (int)(chunk & 1);
+            if (host_clk.capacity > 0) h->path_tail = host_clk.tail;
         }
+        done += chunk;
     }
-    if (!export_accel) h->cur ^= 1;
+    if (clk0 && !export_accel) *clk0 = host_clk;
     return 0;
 }
 
-// peer-memory exchange: make the stream wait until every peer's positions of
-// the current step have landed in this device's pos[cur]
+// make the stream wait until every peer's positions of the current step have landed in
+// this device's pos[cur] (peer-memory exchange only)
 int enqueue_wait_peers(gravity_cuda_t *h, DeviceCtx &c)
 {
-    if (!(h->opt_exchange == 1 && h->nranks > 1)) return 0;
-    k_wait_peers<<<1, 32, 0, c.stream>>>(c.flags, h->step_id, c.rank, h->nranks, c.status);
+    if (!p2p_active(h)) return 0;
+    k_wait_peers<<<1, 32, 0, c.stream>>>(peer_exchange(h, c, true), h->step_id, wait_policy(h, c));
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
 
-int check_exchange_status(gravity_cuda_t *h)
+// A device-side wait that gave up leaves the state partly advanced: report it once and
+// refuse further work (fail-stop; see "spin_timeout_ms" in gravity_cuda.h).
+int check_status(gravity_cuda_t *h)
 {
-    if (!(h->opt_exchange == 1 && h->nranks > 1)) return 0;
     for (DeviceCtx &c : h->ctx) {
         unsigned int st = 0;
         CUDA_TRY(h, cudaSetDevice(c.device));
         CUDA_TRY(h, cudaMemcpy(&st, c.status, sizeof(st), cudaMemcpyDeviceToHost));
-        if (st != 0) return fail(h, "peer-memory exchange timed out on rank %d: a peer never published its step", c.rank);
+        if (st != 0) {
+            h->dead = true;
+            return fail(h, st == kStatusPeerTimeout
+                               ? "peer-memory exchange timed out on rank %d: a peer never published its step; handle is dead"
+                               : "step kernel timed out on rank %d waiting for an i-block of its own device; handle is dead",
+                        c.rank);
+        }
     }
     return 0;
 }
@@ -591,6 +693,10 @@ int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
     CUDA_TRY(h, cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreate(&c.ev_start));
     CUDA_TRY(h, cudaEventCreate(&c.ev_stop));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
+    int khz = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c.device));
+    c.clock_khz = khz;
     c.i0 = (int64_t)c.rank * h->chunk;
     c.n_local = std::max<int64_t>(0, std::min<int64_t>(h->chunk, h->n - c.i0));
     CUDA_TRY(h, cudaMalloc(&c.pos[0], sizeof(double2) * h->npad));
@@ -598,7 +704,7 @@ int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
     CUDA_TRY(h, cudaMalloc(&c.mass, sizeof(double) * h->npad));
     CUDA_TRY(h, cudaMalloc(&c.vel, sizeof(double2) * h->chunk));
     CUDA_TRY(h, cudaMalloc(&c.accel, sizeof(double2) * h->chunk));
-    CUDA_TRY(h, cudaMalloc(&c.stage, sizeof(double) * 4 * h->npad));
+    CUDA_TRY(h, cudaMalloc(&c.stage, sizeof(double) * 5 * h->npad));
     CUDA_TRY(h, cudaMalloc(&c.tile_mass, sizeof(double) * (h->npad / kTile)));
     CUDA_TRY(h, cudaMalloc(&c.gather_tmp, sizeof(double2) * h->npad));
     CUDA_TRY(h, cudaMalloc(&c.flags, sizeof(unsigned long long) * kMaxPeers));
@@ -667,7 +773,8 @@ static int create_common(gravity_cuda_t **out, int64_t n, int nranks, bool singl
     if (!out) return fail(nullptr, "out is NULL");
     *out = nullptr;
     if (n < 1) return fail(nullptr, "n must be >= 1 (got %lld)", (long long)n);
-    if (nranks < 1 || nranks > 64) return fail(nullptr, "number of GPUs must be 1..64 (got %d)", nranks);
+    if (nranks < 1 || nranks > kMaxPeers)
+        return fail(nullptr, "number of GPUs must be 1..%d, the GPUs of one NVSwitch box (got %d)", kMaxPeers, nranks);
     gravity_cuda_t *h = new (std::nothrow) gravity_cuda();
     if (!h) return fail(nullptr, "out of host memory");
     h->single_process = single_process;
@@ -740,12 +847,24 @@ int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nran
 void gravity_cuda_destroy(gravity_cuda_t *h)
 {
     if (!h) return;
+    // Nothing may be freed while a peer can still store into it.  With the peer-memory
+    // exchange a peer's last step kernel writes this device's position buffer and flags
+    // until it has published the handle's current step: wait for that (bounded by the
+    // spin timeout), then for this device's own work.  In rank mode destroy is therefore
+    // collective in the same sense as step: call it on every rank after the same steps.
     for (DeviceCtx &c : h->ctx) {
         cudaSetDevice(c.device);
-        if (c.stream) cudaStreamSynchronize(c.stream);
+        if (c.stream) {
+            if (p2p_active(h) && h->p2p_connected && c.flags && c.status && !h->dead) {
+                k_wait_peers<<<1, 32, 0, c.stream>>>(peer_exchange(h, c, true), h->step_id, wait_policy(h, c));
+            }
+            cudaStreamSynchronize(c.stream);
+        }
+    }
+    cudaGetLastError();
+    for (DeviceCtx &c : h->ctx) {
+        cudaSetDevice(c.device);
         if (c.comm) ncclCommDestroy(c.comm);
-        cudaFree(c.pos[0]); cudaFree(c.pos[1]); cudaFree(c.mass); cudaFree(c.vel); cudaFree(c.accel);
-        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.tile_mass);
         for (int r = 0; r < kMaxPeers; ++r) {
             if (c.ipc_opened[r]) {
                 cudaIpcCloseMemHandle(c.peer_pos[0][r]);
@@ -753,12 +872,15 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
                 cudaIpcCloseMemHandle(c.peer_flags[r]);
             }
         }
-        cudaFree(c.gather_tmp); cudaFree(c.flags); cudaFree(c.commit_counter); cudaFree(c.status); cudaFree(c.partial); cudaFree(c.seg);
-        cudaFree(c.cta_seg_begin); cudaFree(c.iblock_seg_begin);
-        cudaFree(c.iblock_arrivals); cudaFree(c.iblocks_done);
+        cudaFree(c.pos[0]); cudaFree(c.pos[1]); cudaFree(c.mass); cudaFree(c.vel); cudaFree(c.accel);
+        cudaFree(c.kin); cudaFree(c.pot); cudaFree(c.stage); cudaFree(c.tile_mass); cudaFree(c.ring);
+        cudaFree(c.gather_tmp); cudaFree(c.flags); cudaFree(c.commit_counter); cudaFree(c.status);
+        cudaFree(c.partial_hi); cudaFree(c.partial_lo); cudaFree(c.seg); cudaFree(c.cta_seg_begin);
+        cudaFree(c.iblock_seg_begin); cudaFree(c.counters); cudaFree(c.trace);
         for (cudaEvent_t e : c.kev) cudaEventDestroy(e);
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_stop) cudaEventDestroy(c.ev_stop);
+        if (c.ev_copy) cudaEventDestroy(c.ev_copy);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
     delete h;
@@ -867,7 +989,34 @@ int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
             if (gravity_cuda_p2p_connect(h, nullptr, 0) != 0) return -1;
         }
         if (rank_barrier(h) != 0) return -1;
+        if (value == 1 && h->nranks > 1) {
+            // the flags count absolute steps; with the all-gather nobody published any, so every
+            // rank writes the step all ranks are at (this call is collective) into its own array
+            std::vector<unsigned long long> now(kMaxPeers, h->step_id);
+            for (DeviceCtx &c : h->ctx) {
+                CUDA_TRY(h, cudaSetDevice(c.device));
+                CUDA_TRY(h, cudaMemcpy(c.flags, now.data(), sizeof(unsigned long long) * kMaxPeers, cudaMemcpyHostToDevice));
+            }
+            if (rank_barrier(h) != 0) return -1;
+        }
         h->opt_exchange = (int)value;
+    } else if (!strcmp(key, "debug_shard_of")) {
+        // developer aid for tuning the small-shard regime on one GPU: the device updates only the
+        // bodies rank 0 of `value` ranks would own, with that rank's launch plan and no exchange
+        if (h->nranks != 1 || value < 1 || value > kMaxPeers) return fail(h, "debug_shard_of needs a 1-GPU handle and 1..%d", kMaxPeers);
+        h->opt_debug_shard_of = (int)value;
+        const int64_t per = (h->n + value - 1) / value;
+        h->ctx[0].n_local = std::min<int64_t>(h->n, std::max<int64_t>(kTile, ((per + kTile - 1) / kTile) * kTile));
+    } else if (!strcmp(key, "persistent")) {
+        h->opt_persistent = value ? 1 : 0;
+    } else if (!strcmp(key, "trace")) {
+        h->opt_trace = value ? 1 : 0;
+    } else if (!strcmp(key, "spin_timeout_ms")) {
+        if (value < 0) return fail(h, "spin_timeout_ms must be >= 0 (0: wait for ever)");
+        h->opt_spin_timeout_ms = value;
+    } else if (!strcmp(key, "download_scope")) {
+        if (value != 0 && value != 1) return fail(h, "download_scope must be 0 (all bodies) or 1 (own shard)");
+        h->opt_download_scope = (int)value;
     } else {
         return fail(h, "unknown option '%s'", key);
     }
@@ -879,30 +1028,100 @@ int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, 
                         const double *vx, const double *vy)
 {
     if (!h) return fail(nullptr, "upload: NULL handle");
-    if (!mass || !x || !y || !vx || !vy) return fail(h, "upload: NULL array");
-    if (rank_barrier(h) != 0) return -1;
-    const int64_t n = h->n, np = h->npad;
-    h->cur = 0;
+    if (h->dead) return fail(h, "the handle is dead: a device-side wait timed out earlier");
+    if (!x || !y || !vx || !vy) return fail(h, "upload: NULL array");
+    if (!mass && !h->mass_uploaded) return fail(h, "upload: mass may only be NULL after an earlier upload set the masses");
+    const int64_t np = h->npad;
+    // Every device copies only its OWN shard from the host (40*N bytes cross PCIe in
+    // total, whatever the number of GPUs); the devices then complete each other's
+    // position and mass arrays with one in-place all-gather over NVLink.  That
+    // collective also orders this upload after every peer's earlier step kernels,
+    // which may still be storing into this device's buffers.
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
         double *sx = c.stage, *sy = c.stage + np, *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
-        CUDA_TRY(h, cudaMemcpyAsync(sx, x, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
-        CUDA_TRY(h, cudaMemcpyAsync(sy, y, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
-        CUDA_TRY(h, cudaMemcpyAsync(c.mass, mass, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
-        k_pack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(sx, sy, c.pos[0], n);
-        const int n_tile = (int)(np / kTile);
-        k_tile_mass<<<(n_tile + 3) / 4, 128, 0, c.stream>>>(c.mass, c.tile_mass, n_tile);
-        h->launches += 2;
         if (c.n_local > 0) {
-            CUDA_TRY(h, cudaMemcpyAsync(svx, vx + c.i0, sizeof(double) * c.n_local, cudaMemcpyHostToDevice, c.stream));
-            CUDA_TRY(h, cudaMemcpyAsync(svy, vy + c.i0, sizeof(double) * c.n_local, cudaMemcpyHostToDevice, c.stream));
-            k_pack_pairs<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(svx, svy, c.vel, c.n_local);
+            const size_t bytes = sizeof(double) * c.n_local;
+            CUDA_TRY(h, cudaMemcpyAsync(sx, x + c.i0, bytes, cudaMemcpyHostToDevice, c.stream));
+            CUDA_TRY(h, cudaMemcpyAsync(sy, y + c.i0, bytes, cudaMemcpyHostToDevice, c.stream));
+            CUDA_TRY(h, cudaMemcpyAsync(svx, vx + c.i0, bytes, cudaMemcpyHostToDevice, c.stream));
+            CUDA_TRY(h, cudaMemcpyAsync(svy, vy + c.i0, bytes, cudaMemcpyHostToDevice, c.stream));
+            if (mass) CUDA_TRY(h, cudaMemcpyAsync(c.mass + c.i0, mass + c.i0, bytes, cudaMemcpyHostToDevice, c.stream));
+        }
+        CUDA_TRY(h, cudaEventRecord(c.ev_copy, c.stream));          // the host arrays are free again after this
+        if (c.n_local > 0) {
+            const unsigned grid = (unsigned)((c.n_local + 255) / 256);
+            k_pack_pairs<<<grid, 256, 0, c.stream>>>(sx, sy, c.pos[0] + c.i0, c.n_local);
+            k_pack_pairs<<<grid, 256, 0, c.stream>>>(svx, svy, c.vel, c.n_local);
+            h->launches += 2;
+            CUDA_TRY(h, cudaGetLastError());
+        }
+    }
+    if (h->nranks > 1) {
+        NCCL_TRY(h, ncclGroupStart());
+        for (DeviceCtx &c : h->ctx) {
+            NCCL_TRY(h, ncclAllGather(c.pos[0] + c.i0, c.pos[0], (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
+            if (mass) NCCL_TRY(h, ncclAllGather(c.mass + c.i0, c.mass, (size_t)h->chunk, ncclDouble, c.comm, c.stream));
+        }
+        NCCL_TRY(h, ncclGroupEnd());
+    }
+    if (mass) {
+        for (DeviceCtx &c : h->ctx) {
+            CUDA_TRY(h, cudaSetDevice(c.device));
+            const int n_tile = (int)(np / kTile);
+            k_tile_mass<<<(n_tile + 3) / 4, 128, 0, c.stream>>>(c.mass, c.tile_mass, n_tile);
             h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
         }
-        CUDA_TRY(h, cudaGetLastError());
-        }
-    if (sync_all(h) != 0) return -1;
+    }
+    h->cur = 0;
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        CUDA_TRY(h, cudaEventSynchronize(c.ev_copy));
+    }
+    if (mass) h->mass_uploaded = true;
     h->uploaded = true;
+    return 0;
+}
+
+// positions / velocities / accelerations of the caller's own shard(s): device -> host
+static int download_shards(gravity_cuda_t *h, const double2 *(*src)(gravity_cuda_t *, DeviceCtx &), bool global_index,
+                           double *a, double *b, int stage_slot)
+{
+    const int64_t np = h->npad;
+    for (DeviceCtx &c : h->ctx) {
+        if (c.n_local == 0) continue;
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        double *sa = c.stage + (size_t)stage_slot * np, *sb = sa + np;
+        const double2 *from = src(h, c) + (global_index ? c.i0 : 0);
+        k_unpack_pairs<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(from, sa, sb, c.n_local);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        if (a) CUDA_TRY(h, cudaMemcpyAsync(a + c.i0, sa, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
+        if (b) CUDA_TRY(h, cudaMemcpyAsync(b + c.i0, sb, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
+    }
+    return 0;
+}
+
+static const double2 *src_pos(gravity_cuda_t *h, DeviceCtx &c) { return c.pos[h->cur]; }
+static const double2 *src_vel(gravity_cuda_t *, DeviceCtx &c) { return c.vel; }
+static const double2 *src_accel(gravity_cuda_t *, DeviceCtx &c) { return c.accel; }
+
+// rank mode, all bodies wanted: gather a sharded double2 array through the scratch buffer
+static int download_gathered(gravity_cuda_t *h, const double2 *shard, double *a, double *b, int stage_slot)
+{
+    const int64_t n = h->n, np = h->npad;
+    DeviceCtx &c = h->ctx[0];
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    double2 *tmp = c.gather_tmp;
+    double *sa = c.stage + (size_t)stage_slot * np, *sb = sa + np;
+    CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, shard, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
+    NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
+    k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(tmp, sa, sb, n);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    if (a) CUDA_TRY(h, cudaMemcpyAsync(a, sa, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    if (b) CUDA_TRY(h, cudaMemcpyAsync(b, sb, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
     return 0;
 }
 
@@ -910,108 +1129,111 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
 {
     if (!h) return fail(nullptr, "download: NULL handle");
     if (!h->uploaded) return fail(h, "download before upload");
-    if (sync_all(h) != 0) return -1;
     const int64_t n = h->n, np = h->npad;
+    // a handle that holds every shard itself, or a caller that asked for its own shard
+    // only ("download_scope" = 1), needs no exchange: every device returns what it owns
+    const bool own_only = h->single_process || h->nranks == 1 || h->opt_download_scope == 1;
     if (x || y) {
-        DeviceCtx &c = h->ctx[0];
-        CUDA_TRY(h, cudaSetDevice(c.device));
-        double *sx = c.stage, *sy = c.stage + np;
-        if (enqueue_wait_peers(h, c) != 0) return -1;
-        k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(c.pos[h->cur], sx, sy, n);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
-        if (x) CUDA_TRY(h, cudaMemcpyAsync(x, sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
-        if (y) CUDA_TRY(h, cudaMemcpyAsync(y, sy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
-    }
-    if (vx || vy) {
-        if (h->single_process || h->nranks == 1) {
-            for (DeviceCtx &c : h->ctx) {
-                if (c.n_local == 0) continue;
-                CUDA_TRY(h, cudaSetDevice(c.device));
-                double *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
-                k_unpack_pairs<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(c.vel, svx, svy, c.n_local);
-                h->launches++;
-                CUDA_TRY(h, cudaGetLastError());
-                if (vx) CUDA_TRY(h, cudaMemcpyAsync(vx + c.i0, svx, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
-                if (vy) CUDA_TRY(h, cudaMemcpyAsync(vy + c.i0, svy, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
-            }
+        if (own_only) {
+            if (download_shards(h, src_pos, true, x, y, 0) != 0) return -1;
         } else {
-            // rank mode: gather the velocity shards through the spare position buffer
             DeviceCtx &c = h->ctx[0];
             CUDA_TRY(h, cudaSetDevice(c.device));
-            double2 *tmp = c.gather_tmp;
-            double *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
-            CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.vel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
-            NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
-            k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(tmp, svx, svy, n);
+            double *sx = c.stage, *sy = c.stage + np;
+            if (enqueue_wait_peers(h, c) != 0) return -1;
+            k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(c.pos[h->cur], sx, sy, n);
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
-            if (vx) CUDA_TRY(h, cudaMemcpyAsync(vx, svx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
-            if (vy) CUDA_TRY(h, cudaMemcpyAsync(vy, svy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+            if (x) CUDA_TRY(h, cudaMemcpyAsync(x, sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+            if (y) CUDA_TRY(h, cudaMemcpyAsync(y, sy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+        }
+    }
+    if (vx || vy) {
+        if (own_only) {
+            if (download_shards(h, src_vel, false, vx, vy, 2) != 0) return -1;
+        } else {
+            if (download_gathered(h, h->ctx[0].vel, vx, vy, 2) != 0) return -1;
         }
     }
     if (sync_all(h) != 0) return -1;
-    return check_exchange_status(h);
+    return check_status(h);
+}
+
+// ---- the hot path ------------------------------------------------------------------------
+
+// N <= 1024 on one device in STRICT mode: the whole batch in one launch of a multi-step kernel
+static int launch_small_strict(gravity_cuda_t *h, double dtd, int64_t nsteps, StepClock *clk)
+{
+    DeviceCtx &c = h->ctx[0];
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    int coop = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
+    StepClock dev_clk = *clk;
+    dev_clk.ring = c.ring;
+    hot_event(h, c);
+    if (h->n <= kPairMax) {
+        const int threads = (int)(((h->n * h->n + 31) / 32) * 32);
+        k_small_strict_steps_pairs<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
+                                                                (long long)nsteps, dev_clk);
+    } else if (coop) {
+        CoopParams P;
+        P.pos[0] = c.pos[0];
+        P.pos[1] = c.pos[1];
+        P.vel = c.vel;
+        P.mass = c.mass;
+        P.n = (int)h->n;
+        P.bodies_per_cta = (int)((h->n + c.num_sms - 1) / c.num_sms);
+        P.cur = h->cur;
+        P.dt = dtd;
+        P.nsteps = (long long)nsteps;
+        P.clock = dev_clk;
+        const int grid = (int)((h->n + P.bodies_per_cta - 1) / P.bodies_per_cta);
+        const size_t smem = coop_smem_bytes(P.n, P.bodies_per_cta);
+        CUDA_TRY(h, cudaFuncSetAttribute(k_strict_coop_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void *args[] = {&P};
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)k_strict_coop_steps, dim3(grid), dim3(kCoopThreads),
+                                                args, smem, c.stream));
+        h->cur ^= (int)(nsteps & 1);      // the state ends in the other buffer after an odd number of steps
+    } else {
+        const int threads = (int)(((h->n + 31) / 32) * 32);
+        k_small_strict_steps<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
+                                                          (long long)nsteps, dev_clk);
+    }
+    hot_event(h, c);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    for (int64_t k = 0; k < nsteps; ++k) clock_tick(*clk);
+    if (clk->capacity > 0) h->path_tail = clk->tail;
+    h->step_id += (unsigned long long)nsteps;
+    return 0;
+}
+
+static int step_impl(gravity_cuda_t *h, int32_t dt, int64_t nsteps, StepClock *clk)
+{
+    if (!h->uploaded) return fail(h, "step before upload");
+    if (nsteps < 0) return fail(h, "nsteps must be >= 0");
+    if (h->dead) return fail(h, "the handle is dead: a device-side wait timed out earlier");
+    if (nsteps == 0) return 0;
+    const double dtd = (double)dt;
+    if (effective_kernel(h) == GRAVITY_CUDA_KERNEL_STRICT && h->nranks == 1 && h->n <= kSmallMax)
+        return launch_small_strict(h, dtd, nsteps, clk);
+    return enqueue_steps(h, dtd, (long long)nsteps, false, clk);
 }
 
 int gravity_cuda_step_async(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
 {
     if (!h) return fail(nullptr, "step: NULL handle");
-    if (!h->uploaded) return fail(h, "step before upload");
-    if (nsteps < 0) return fail(h, "nsteps must be >= 0");
-    if (nsteps == 0) return 0;
-    const double dtd = (double)dt;
-    const int kernel = effective_kernel(h);
-    if (kernel == GRAVITY_CUDA_KERNEL_STRICT && h->nranks == 1 && h->n <= kSmallMax) {
-        // the whole batch in one single-CTA launch
-        DeviceCtx &c = h->ctx[0];
-        CUDA_TRY(h, cudaSetDevice(c.device));
-        int coop = 0;
-        CUDA_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device));
-        hot_event(h, c);
-        if (h->n <= kPairMax) {
-            const int threads = (int)(((h->n * h->n + 31) / 32) * 32);
-            k_small_strict_steps_pairs<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
-                                                                    (long long)nsteps);
-        } else if (coop) {
-            CoopParams P;
-            P.pos[0] = c.pos[0];
-            P.pos[1] = c.pos[1];
-            P.vel = c.vel;
-            P.mass = c.mass;
-            P.n = (int)h->n;
-            P.bodies_per_cta = (int)((h->n + c.num_sms - 1) / c.num_sms);
-            P.cur = h->cur;
-            P.dt = dtd;
-            P.nsteps = (long long)nsteps;
-            const int grid = (int)((h->n + P.bodies_per_cta - 1) / P.bodies_per_cta);
-            const size_t smem = coop_smem_bytes(P.n, P.bodies_per_cta);
-            CUDA_TRY(h, cudaFuncSetAttribute(k_strict_coop_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            void *args[] = {&P};
-            CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)k_strict_coop_steps, dim3(grid), dim3(kCoopThreads),
-                                                    args, smem, c.stream));
-            h->cur ^= (int)(nsteps & 1);      // the state ends in the other buffer after an odd number of steps
-        } else {
-            const int threads = (int)(((h->n + 31) / 32) * 32);
-            k_small_strict_steps<<<1, threads, 0, c.stream>>>(c.pos[h->cur], c.vel, c.mass, (int)h->n, dtd,
-                                                              (long long)nsteps);
-        }
-        hot_event(h, c);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
-        return 0;
-    }
-    for (int64_t s = 0; s < nsteps; ++s) {
-        if (enqueue_evaluation(h, dtd, false, true) != 0) return -1;
-    }
-    return 0;
+    StepClock off;
+    memset(&off, 0, sizeof(off));
+    off.dt = dt;
+    return step_impl(h, dt, nsteps, &off);
 }
 
 int gravity_cuda_sync(gravity_cuda_t *h)
 {
     if (!h) return fail(nullptr, "sync: NULL handle");
     if (sync_all(h) != 0) return -1;
-    return check_exchange_status(h);
+    return check_status(h);
 }
 
 int gravity_cuda_step(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
@@ -1020,39 +1242,104 @@ int gravity_cuda_step(gravity_cuda_t *h, int32_t dt, int64_t nsteps)
     return gravity_cuda_sync(h);
 }
 
+// ---- PATH ring on the device (sim_gravity.c:1230-1260) -------------------------------------
+
+int gravity_cuda_path_enable(gravity_cuda_t *h, int64_t capacity)
+{
+    if (!h) return fail(nullptr, "path_enable: NULL handle");
+    if (capacity < 0) return fail(h, "path_enable: capacity must be >= 0");
+    if (sync_all(h) != 0) return -1;
+    for (DeviceCtx &c : h->ctx) {
+        CUDA_TRY(h, cudaSetDevice(c.device));
+        cudaFree(c.ring);
+        c.ring = nullptr;
+        if (capacity > 0) CUDA_TRY(h, cudaMalloc(&c.ring, sizeof(double2) * (size_t)capacity * h->npad));
+    }
+    h->path_capacity = capacity;
+    h->path_tail = 0;
+    return 0;
+}
+
+int gravity_cuda_step_path(gravity_cuda_t *h, int32_t dt, int64_t nsteps, int64_t sim_time, int32_t *last_day,
+                           int64_t *path_tail)
+{
+    if (!h) return fail(nullptr, "step_path: NULL handle");
+    if (!last_day) return fail(h, "step_path: last_day is NULL");
+    if (h->path_capacity <= 0) return fail(h, "step_path before path_enable");
+    if (dt < 1 || sim_time < 0) return fail(h, "step_path needs dt >= 1 and sim_time >= 0 (the reference never has others)");
+    StepClock clk = make_clock(h, h->ctx[0], dt, sim_time, *last_day, true);
+    if (step_impl(h, dt, nsteps, &clk) != 0) return -1;
+    if (gravity_cuda_sync(h) != 0) return -1;
+    *last_day = clk.last_day;
+    if (path_tail) *path_tail = h->path_tail;
+    return 0;
+}
+
+int gravity_cuda_path_read(gravity_cuda_t *h, int64_t first, int64_t count, double *x, double *y)
+{
+    if (!h) return fail(nullptr, "path_read: NULL handle");
+    if (h->path_capacity <= 0) return fail(h, "path_read before path_enable");
+    if (count < 0 || first < 0 || first + count > h->path_tail)
+        return fail(h, "path_read: samples %lld..%lld were never taken (path_tail = %lld)", (long long)first,
+                    (long long)(first + count), (long long)h->path_tail);
+    if (h->path_tail - first > h->path_capacity)
+        return fail(h, "path_read: sample %lld has been overwritten (ring of %lld rows, path_tail = %lld)",
+                    (long long)first, (long long)h->path_capacity, (long long)h->path_tail);
+    if (count == 0) return 0;
+    if (!x || !y) return fail(h, "path_read: NULL array");
+    return no_throw(h, [&]() -> int {
+        // every device holds the ring columns of its own shard; rows are copied as they lie
+        // (interleaved X,Y) and split on the host -- PATH is display data, a few rows per call
+        std::vector<double2> row((size_t)h->chunk);
+        if (sync_all(h) != 0) return -1;
+        const bool own_only = h->single_process || h->nranks == 1 || h->opt_download_scope == 1;
+        for (int64_t k = 0; k < count; ++k) {
+            const int64_t r = (first + k) % h->path_capacity;
+            if (own_only) {
+                for (DeviceCtx &c : h->ctx) {
+                    if (c.n_local == 0) continue;
+                    CUDA_TRY(h, cudaSetDevice(c.device));
+                    CUDA_TRY(h, cudaMemcpy(row.data(), c.ring + (size_t)r * h->npad + c.i0, sizeof(double2) * c.n_local,
+                                           cudaMemcpyDeviceToHost));
+                    for (int64_t i = 0; i < c.n_local; ++i) {
+                        x[k * h->n + c.i0 + i] = row[(size_t)i].x;
+                        y[k * h->n + c.i0 + i] = row[(size_t)i].y;
+                    }
+                }
+            } else {
+                DeviceCtx &c = h->ctx[0];
+                CUDA_TRY(h, cudaSetDevice(c.device));
+                double2 *ring_row = c.ring + (size_t)r * h->npad;
+                NCCL_TRY(h, ncclAllGather(ring_row + c.i0, ring_row, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
+                CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+                for (int64_t i0 = 0; i0 < h->n; i0 += h->chunk) {
+                    const int64_t cnt = std::min<int64_t>(h->chunk, h->n - i0);
+                    CUDA_TRY(h, cudaMemcpy(row.data(), ring_row + i0, sizeof(double2) * cnt, cudaMemcpyDeviceToHost));
+                    for (int64_t i = 0; i < cnt; ++i) {
+                        x[k * h->n + i0 + i] = row[(size_t)i].x;
+                        y[k * h->n + i0 + i] = row[(size_t)i].y;
+                    }
+                }
+            }
+        }
+        return 0;
+    });
+}
+
 int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay)
 {
     if (!h) return fail(nullptr, "accel: NULL handle");
     if (!h->uploaded) return fail(h, "accel before upload");
     if (!ax || !ay) return fail(h, "accel: NULL array");
-    if (enqueue_evaluation(h, (double)dt, true, false) != 0) return -1;
-    if (sync_all(h) != 0) return -1;
-    const int64_t n = h->n, np = h->npad;
-    if (h->single_process || h->nranks == 1) {
-        for (DeviceCtx &c : h->ctx) {
-            if (c.n_local == 0) continue;
-            CUDA_TRY(h, cudaSetDevice(c.device));
-            double *sx = c.stage, *sy = c.stage + np;
-            k_unpack_pairs<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(c.accel, sx, sy, c.n_local);
-            h->launches++;
-            CUDA_TRY(h, cudaGetLastError());
-            CUDA_TRY(h, cudaMemcpyAsync(ax + c.i0, sx, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
-            CUDA_TRY(h, cudaMemcpyAsync(ay + c.i0, sy, sizeof(double) * c.n_local, cudaMemcpyDeviceToHost, c.stream));
-        }
+    if (enqueue_steps(h, (double)dt, 1, true, nullptr) != 0) return -1;
+    const bool own_only = h->single_process || h->nranks == 1 || h->opt_download_scope == 1;
+    if (own_only) {
+        if (download_shards(h, src_accel, false, ax, ay, 0) != 0) return -1;
     } else {
-        DeviceCtx &c = h->ctx[0];
-        CUDA_TRY(h, cudaSetDevice(c.device));
-        double2 *tmp = c.gather_tmp;
-        double *sx = c.stage, *sy = c.stage + np;
-        CUDA_TRY(h, cudaMemcpyAsync(tmp + c.i0, c.accel, sizeof(double2) * h->chunk, cudaMemcpyDeviceToDevice, c.stream));
-        NCCL_TRY(h, ncclAllGather(tmp + c.i0, tmp, (size_t)h->chunk * 2, ncclDouble, c.comm, c.stream));
-        k_unpack_pairs<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(tmp, sx, sy, n);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, cudaMemcpyAsync(ax, sx, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
-        CUDA_TRY(h, cudaMemcpyAsync(ay, sy, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+        if (download_gathered(h, h->ctx[0].accel, ax, ay, 0) != 0) return -1;
     }
-    return sync_all(h);
+    if (sync_all(h) != 0) return -1;
+    return check_status(h);
 }
 
 int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size_t off_x, size_t off_y,
@@ -1249,6 +1536,20 @@ int gravity_cuda_plan_probe(int64_t n, int nranks, int rank, int num_sms, int th
     return no_throw(nullptr, [&] {
         return plan_probe_impl(n, nranks, rank, num_sms, threads, bpt, ctas_per_sm, info, seg_out, seg_cap);
     });
+}
+
+int gravity_cuda_trace_read(gravity_cuda_t *h, uint64_t *stamps, int64_t cap_ctas, int64_t *n_cta)
+{
+    if (!h || !n_cta) return fail(h, "trace_read: NULL argument");
+    DeviceCtx &c = h->ctx[0];
+    if (!c.trace) return fail(h, "trace_read: set option \"trace\" = 1 before the first step");
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaStreamSynchronize(c.stream));
+    *n_cta = c.phase[0].n_cta;
+    const int64_t rows = std::min<int64_t>(cap_ctas, c.phase[0].n_cta);
+    if (stamps && rows > 0)
+        CUDA_TRY(h, cudaMemcpy(stamps, c.trace, sizeof(uint64_t) * (size_t)rows * kTraceEvents, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int gravity_cuda_launch_count(const gravity_cuda_t *h, int64_t *launches)

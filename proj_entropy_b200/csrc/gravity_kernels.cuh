@@ -26,22 +26,57 @@ constexpr int    kLookahead   = 2;       // tiles in flight ahead of the consume
 constexpr int    kSmallMax    = 1024;    // largest N of the single-CTA kernel
 constexpr double kG           = 6.673E-11;   // sim_gravity.c:29
 constexpr double kPadCoord    = 1.0e150;     // parking spot of padding bodies
-constexpr int    kMaxPeers    = 16;          // ranks of the peer-memory exchange
-constexpr long long kSpinTimeoutCycles = 20000000000LL;   // ~10 s: give up instead of hanging
+constexpr int    kMaxPeers    = 8;           // ranks of the peer-memory exchange (one NVSwitch box)
+constexpr int    kTraceEvents = 8;           // per-CTA time stamps of the optional trace
+
+// status word values (0 = fine).  Once it is non-zero every kernel of the handle
+// stops storing and publishing: the handle is fail-stop.
+constexpr unsigned int kStatusPeerTimeout  = 1u;   // a peer never published its step
+constexpr unsigned int kStatusLocalTimeout = 2u;   // an i-block of this device never got ready
+
+// The commit block's clock (sim_gravity.c:1232-1236, :1255-1260), carried into the
+// kernels that run many steps per launch so that the once-per-simulated-day PATH
+// sample needs no host round trip.  `day`/`rem` describe sim_time BEFORE the
+// step's `sim_time += DT`, which is what the reference tests.
+struct StepClock {
+    long long day;        // sim_time / 86400
+    long long rem;        // sim_time % 86400
+    long long tail;       // samples taken so far (path_tail); ring row = tail % capacity
+    long long capacity;   // rows of the ring; 0 = PATH sampling off
+    double2  *ring;       // [capacity][npad] positions, one row per sample
+    long long npad;
+    int32_t   last_day;   // function-static in the reference
+    int32_t   dt;         // > 0
+};
+
+// One commit's worth of clock: returns the ring row to sample into, or -1.
+__host__ __device__ inline long long clock_tick(StepClock &c)
+{
+    long long row = -1;
+    if (c.capacity > 0) {
+        const int32_t day = (int32_t)c.day;                      // `int32_t day = sim.sim_time/86400` (:1234)
+        if (day != c.last_day) row = c.tail++ % c.capacity;      // :1235, :1248-1251, :1258-1260
+        c.last_day = day;                                        // :1236
+        c.rem += c.dt;                                           // :1255
+        if (c.rem >= 86400) {
+            const long long q = c.rem / 86400;
+            c.day += q;
+            c.rem -= q * 86400;
+        }
+    }
+    return row;
+}
 
 // Peer-memory exchange (replaces the NCCL all-gather when connected): the step
 // kernel stores every new position into each peer's copy of pos_next over
-// NVLink as soon as its i-block is committed and, when the rank's last i-block
-// is done, publishes its step number in each peer's flag array; the next step's
-// kernel waits, just before it fetches the first tile of other ranks' bodies,
-// until every peer's flag has reached the step it is about to read.
+// NVLink as soon as it is committed and, when the rank's last i-block is done,
+// publishes its step number in each peer's flag array; before a kernel fetches
+// the first tile of other ranks' bodies for a step it waits until every peer's
+// flag has reached that step.
 struct PeerExchange {
-    double2            *peer_next[kMaxPeers];    // pos_next of every rank, as mapped here
+    double2            *peer_pos[2][kMaxPeers];  // both position buffers of every rank, as mapped here
     unsigned long long *peer_flags[kMaxPeers];   // flag array of every rank, as mapped here
     unsigned long long *flags;                   // this rank's own flag array [kMaxPeers]
-    unsigned int       *commit_counter;          // last-CTA detection
-    unsigned int       *status;                  // != 0: a wait timed out
-    unsigned long long  step;                    // commit: value to publish; wait: value required
     int32_t             rank, nranks;
     int32_t             enabled;
     int32_t             reserved;
@@ -55,50 +90,67 @@ struct Segment {
     int32_t slot;         // which partial[] row this segment writes
 };
 
+// Spin-wait policy shared by every kernel that waits on another CTA or GPU.
+struct WaitPolicy {
+    unsigned int *status;          // device word, see kStatus*
+    long long     timeout_cycles;  // 0: wait for ever
+};
+
+// Parameters of the strict row kernel (one launch per step).
 struct CommitParams {
     const double2 *pos_cur;         // time-t positions (all bodies)
     double2       *pos_next;        // time-t+1 positions (all bodies; we write our shard)
     double2       *vel;             // local shard, updated in place
     const double  *mass;
-    const double2 *partial;
-    const int32_t *iblock_seg_begin;    // [n_iblock + 1] partial rows of each i-block
-    int32_t       *iblock_arrivals;     // [n_iblock] segments finished so far (self-resetting)
-    int32_t       *iblocks_done;        // [1] i-blocks committed so far (self-resetting)
-    int32_t        n_iblock;
-    int32_t        reserved;
     double2       *accel_out;       // local shard, used when export_accel
+    double2       *ring_row;        // PATH sample row for this step, or NULL
     int64_t        n;               // real bodies, all shards
     int64_t        i_global0;
     int64_t        n_local;
-    int32_t        iblock_size;     // IB of the accumulate kernel
     int32_t        export_accel;    // 1: write AX,AY and leave the state alone
+    int32_t        cur_next;        // index of pos_next among the two buffers (peer stores)
     double         dt;
-    const unsigned long long *wait_flags;   // strict kernel only: it reads pos_cur itself
-    unsigned long long wait_step;
+    unsigned int  *commit_counter;  // last-CTA detection
+    unsigned long long wait_step;   // peers must have published this step before pos_cur is read
+    unsigned long long publish_step;
+    WaitPolicy     wp;
     PeerExchange   px;
 };
 
-struct AccumParams {
-    const double2 *pos;             // time-t positions of all bodies
+// Parameters of the tiled step kernel.
+struct TiledParams {
+    double2       *pos[2];          // ping-pong positions of ALL bodies; pos[cur] is time t at step 0
     const double  *mass;
-    const double2 *vel;             // local shard
-    double2       *partial;         // [nseg][IB]
+    double2       *vel;             // local shard, updated in place
+    double2       *accel_out;       // local shard, used when export_accel
+    double2       *partial_hi;      // [nseg][IB] per-segment partial sums ...
+    double2       *partial_lo;      // ... and their compensation terms
     const Segment *seg;
     const int32_t *cta_seg_begin;   // [gridDim.x + 1]
+    const int32_t *iblock_seg_begin;    // [n_iblock + 1] partial rows of each i-block
     const double  *tile_mass;       // [n_tile] common mass of a j-tile whose 256 masses are
                                     // bit-identical, NaN otherwise; NULL = never fold
+    // dataflow counters, all monotonic (never reset while the plan lives)
+    unsigned long long *arrivals;       // [n_iblock] partial rows written, all evaluations
+    unsigned long long *slices_done;    // [n_iblock] slices committed, all evaluations
+    unsigned long long *iblock_ready;   // [n_iblock] absolute step number this i-block has reached
+    unsigned long long *iblocks_done;   // [1] i-blocks committed, all evaluations
+    unsigned long long *trace;          // [gridDim.x][kTraceEvents] globaltimer stamps, or NULL
+    unsigned long long  epoch;          // evaluations done with this plan before this launch
+    unsigned long long  step_base;      // absolute step number of the state at launch
+    long long           nsteps;         // steps in this launch (1 when export_accel)
+    int64_t        n;               // real bodies, all shards
     int64_t        i_global0;       // global index of local body 0
     int64_t        n_local;         // real bodies in the local shard
+    int32_t        n_iblock;
+    int32_t        cur;
+    int32_t        export_accel;
+    int32_t        local_tile_begin, local_tile_end;   // j-tiles of this rank's own shard
+    int32_t        reserved;
     double         dt;              // (double)DT
-    // peer-memory exchange: j-tiles outside [local_tile_begin, local_tile_end) hold
-    // other ranks' bodies and may only be fetched once every peer has published
-    // `wait_step`; NULL wait_flags = nothing to wait for
-    const unsigned long long *wait_flags;
-    unsigned int  *wait_status;
-    unsigned long long wait_step;
-    int32_t        wait_rank, wait_nranks;
-    int32_t        local_tile_begin, local_tile_end;
-    CommitParams   cm;              // what the last CTA to finish an i-block does with it
+    StepClock      clock;
+    WaitPolicy     wp;
+    PeerExchange   px;
 };
 
 // ---------------------------------------------------------------------------
@@ -152,7 +204,7 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
 }
 
 // ---------------------------------------------------------------------------
-// Peer-memory exchange helpers
+// Waiting on other CTAs and other GPUs
 // ---------------------------------------------------------------------------
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -162,82 +214,75 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Called by every thread of a CTA before it reads time-t positions: lanes
-// 0..nranks-1 of warp 0 each wait for one peer's flag.  A peer that never arrives
-// is reported through *status after ~10 s instead of hanging the GPU.
-__device__ __forceinline__ void wait_for_peers(const unsigned long long *flags, unsigned long long step,
-                                               int rank, int nranks, unsigned int *status)
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
 {
-    if (flags != nullptr) {
-        const int t = threadIdx.x;
-        if (t < nranks && t != rank) {
-            const long long t0 = clock64();
-            while (ld_acquire_sys(flags + t) < step) {
-                if (clock64() - t0 > kSpinTimeoutCycles) {
-                    if (status) atomicExch(status, 1u);
-                    break;
-                }
-                __nanosleep(64);
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin (one thread) until *p >= target.  Returns false -- after recording `code`
+// in the status word -- when the wait timed out, and at once when another waiter
+// of this handle already gave up, so that one missing producer never hangs the
+// GPU and never lets a kernel commit stale data: callers stop storing on false.
+template <bool SYS>
+__device__ __forceinline__ bool spin_until_reached(const unsigned long long *p, unsigned long long target,
+                                                   const WaitPolicy &wp, unsigned int code)
+{
+    if ((SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p)) >= target) return true;
+    const long long t0 = clock64();
+    unsigned int polls = 0;
+    for (;;) {
+        if ((SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p)) >= target) return true;
+        if ((++polls & 63u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned int *>(wp.status) != 0u) return false;
+            if (wp.timeout_cycles > 0 && clock64() - t0 > wp.timeout_cycles) {
+                atomicCAS(wp.status, 0u, code);
+                return false;
             }
         }
-        __syncthreads();
-        // the tiles are fetched by the async proxy (bulk copies)
-        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __nanosleep(SYS ? 64 : 20);
     }
 }
 
-// The same wait done by ONE thread (the tile producer of the pair kernel, just
-// before it fetches the first tile that holds other ranks' bodies).
-__device__ __forceinline__ void wait_for_peers_one_thread(const unsigned long long *flags, unsigned long long step,
-                                                          int rank, int nranks, unsigned int *status)
+// One thread: every peer has published `step`, i.e. its positions of that step
+// have landed in this device's buffer.  The tiles are then fetched by the async
+// proxy (bulk copies), hence the proxy fence.
+__device__ __forceinline__ bool wait_for_peers_one_thread(const PeerExchange &X, unsigned long long step,
+                                                          const WaitPolicy &wp)
 {
-    const long long t0 = clock64();
-    for (int r = 0; r < nranks; ++r) {
-        if (r == rank) continue;
-        while (ld_acquire_sys(flags + r) < step) {
-            if (clock64() - t0 > kSpinTimeoutCycles) {
-                if (status) atomicExch(status, 1u);
-                break;
-            }
-            __nanosleep(64);
-        }
+    bool ok = true;
+    for (int r = 0; r < X.nranks && ok; ++r) {
+        if (r != X.rank) ok = spin_until_reached<true>(X.flags + r, step, wp, kStatusPeerTimeout);
     }
     asm volatile("fence.proxy.async.global;" ::: "memory");
-}
-
-// Called by every thread of a grid after its stores to the peers (strict rows
-// kernel): when the last CTA gets here all new positions of this rank are visible
-// system-wide and the step number is published to every peer, one lane per peer
-// so that the release stores travel over NVLink side by side.
-__device__ __forceinline__ void publish_to_peers(const PeerExchange &X)
-{
-    __shared__ int s_publish;
-    if (!X.enabled) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const unsigned int prev = atomicAdd(X.commit_counter, 1u);
-        s_publish = (prev == gridDim.x - 1) ? 1 : 0;
-        if (s_publish) *X.commit_counter = 0u;           // ready for the next launch
-        __threadfence();
-    }
-    __syncthreads();
-    if (s_publish && (int)threadIdx.x < X.nranks && (int)threadIdx.x != X.rank) {
-        st_release_sys(X.peer_flags[threadIdx.x] + X.rank, X.step);
-    }
+    return ok;
 }
 
 // Lanes 0..nranks-1 of the calling CTA: publish this rank's step number in
-// every peer's flag array, one lane per peer.
-__device__ __forceinline__ void publish_step(const PeerExchange &X)
+// every peer's flag array, one lane per peer so that the release stores travel
+// over NVLink side by side.
+__device__ __forceinline__ void publish_step(const PeerExchange &X, unsigned long long step)
 {
     if ((int)threadIdx.x < X.nranks && (int)threadIdx.x != X.rank) {
-        st_release_sys(X.peer_flags[threadIdx.x] + X.rank, X.step);
+        st_release_sys(X.peer_flags[threadIdx.x] + X.rank, step);
     }
 }
 
@@ -322,6 +367,25 @@ __device__ __forceinline__ void kick_drift(double sum, double dt, double p, doub
 }
 
 // ---------------------------------------------------------------------------
+// Compensated accumulation
+// ---------------------------------------------------------------------------
+
+// hi + err gains t with the rounding error of the addition kept in err
+// (Knuth's two-sum, 6 additions, branch free, no contraction possible).  Used once
+// per j-tile and body -- 0.03 additions per pair -- and when partial rows are
+// added up, so that a large early term no longer costs every later addition an
+// ulp of ITS size: the sum of N terms carries the error of one 256-term tile sum
+// instead of the reference's N sequential additions.
+__device__ __forceinline__ void two_sum_acc(double &hi, double &err, double t)
+{
+    const double s  = __dadd_rn(hi, t);
+    const double bb = __dsub_rn(s, hi);
+    const double e  = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(t, bb));
+    err = __dadd_rn(err, e);
+    hi  = s;
+}
+
+// ---------------------------------------------------------------------------
 // Commit helpers: repair poisoned bodies, kick + drift, hand the result to the peers
 // ---------------------------------------------------------------------------
 
@@ -329,14 +393,14 @@ __device__ __forceinline__ void kick_drift(double sum, double dt, double p, doub
 // per pair (sqrt, divide, both skips), lanes striding over j, fixed-shape tree
 // reduction (deterministic).  Only bodies whose fast sum came out non-finite
 // get here -- in practice bodies that coincide exactly with another body.
-__device__ inline void block_guarded_body(const CommitParams &P, int64_t gi, double px, double py,
-                                          double *s_red, double &sx, double &sy)
+__device__ inline void block_guarded_body(const double2 *pos_cur, const double *mass, int64_t n, int64_t gi,
+                                          double px, double py, double *s_red, double &sx, double &sy)
 {
     double tx = 0.0, ty = 0.0;
-    for (int64_t j = threadIdx.x; j < P.n; j += blockDim.x) {
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
         if (j == gi) continue;                            // sim_gravity.c:1191
-        const double2 pj = P.pos_cur[j];
-        pair_strict(pj.x, pj.y, P.mass[j], px, py, tx, ty);
+        const double2 pj = __ldcg(pos_cur + j);
+        pair_strict(pj.x, pj.y, mass[j], px, py, tx, ty);
     }
     s_red[threadIdx.x]              = tx;
     s_red[blockDim.x + threadIdx.x] = ty;
@@ -353,11 +417,15 @@ __device__ inline void block_guarded_body(const CommitParams &P, int64_t gi, dou
     __syncthreads();
 }
 
-__device__ __forceinline__ void commit_body(const CommitParams &P, int64_t li, double sx, double sy)
+// Kick + drift of one body and the hand-over of its new position: to this
+// device's next buffer, to every peer's (barrier B2 + the commit copy,
+// sim_gravity.c:1226, :1242-1245) and, on a day change, to the PATH ring (:1248-1251).
+__device__ __forceinline__ void commit_body(const TiledParams &P, const double2 *pos_cur, int nxt, int64_t li,
+                                            double sx, double sy, long long ring_row)
 {
     const int64_t gi = P.i_global0 + li;
-    const double2 p  = P.pos_cur[gi];
-    const double2 v  = P.vel[li];
+    const double2 p  = __ldcg(pos_cur + gi);
+    const double2 v  = __ldcg(P.vel + li);
     double nx, ny, nvx, nvy, ax, ay;
     kick_drift(sx, P.dt, p.x, v.x, nx, nvx, ax);
     kick_drift(sy, P.dt, p.y, v.y, ny, nvy, ay);
@@ -365,114 +433,48 @@ __device__ __forceinline__ void commit_body(const CommitParams &P, int64_t li, d
         P.accel_out[li] = make_double2(ax, ay);          // sim_gravity.c:1207-1208
     } else {
         const double2 pn = make_double2(nx, ny);
-        P.pos_next[gi] = pn;                             // NEXT_X, NEXT_Y  (:1218-1219)
+        P.pos[nxt][gi] = pn;                             // NEXT_X, NEXT_Y  (:1218-1219)
         P.vel[li]      = make_double2(nvx, nvy);         // NEXT_VX, NEXT_VY (:1220-1221)
         if (P.px.enabled) {
-            // barrier B2 + the commit copy (:1226, :1242-1245): every peer gets
-            // the new position straight into its own pos_next over NVLink
             for (int r = 0; r < P.px.nranks; ++r) {
-                if (r != P.px.rank) P.px.peer_next[r][gi] = pn;
+                if (r != P.px.rank) P.px.peer_pos[nxt][r][gi] = pn;
             }
         }
-    }
-}
-
-// Executed by the whole CTA that finished an i-block last: add up the partial
-// rows in a fixed order (run-to-run deterministic), redo poisoned bodies on the
-// guarded path, kick + drift, store to self and peers, and publish the step when
-// this was the rank's last i-block.  Kept out of line so that it does not disturb
-// the register allocation of the pair loop.
-template <int THREADS, int R>
-__device__ __noinline__ void commit_iblock(const AccumParams &P, int iblock, double *s_red, int *s_bad, int *s_nbad)
-{
-    constexpr int IB  = THREADS * R;
-    const int     tid = threadIdx.x;
-    const int64_t li0 = (int64_t)iblock * IB;
-    const int     row0 = P.cm.iblock_seg_begin[iblock];
-    const int     row1 = P.cm.iblock_seg_begin[iblock + 1];
-    if (tid == 0) P.cm.iblock_arrivals[iblock] = 0;              // ready for the next launch
-
-    double sx[R], sy[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        sx[r] = 0.0;
-        sy[r] = 0.0;
-        for (int row = row0; row < row1; ++row) {
-            const double2 part = __ldcg(P.partial + (size_t)row * IB + r * THREADS + tid);
-            sx[r] += part.x;
-            sy[r] += part.y;
-        }
-    }
-    bool any_bad = false;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int64_t li = li0 + (int64_t)r * THREADS + tid;
-        any_bad = any_bad || (li < P.n_local && !(isfinite(sx[r]) && isfinite(sy[r])));
-    }
-    if (__syncthreads_or(any_bad)) {
-        if (P.wait_flags != nullptr) {
-            // the guarded path reads every body's position, also other ranks'
-            if (tid == 0) wait_for_peers_one_thread(P.wait_flags, P.wait_step, P.wait_rank, P.wait_nranks, P.wait_status);
-            __syncthreads();
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int64_t li  = li0 + (int64_t)r * THREADS + tid;
-            const bool    bad = li < P.n_local && !(isfinite(sx[r]) && isfinite(sy[r]));
-            if (tid == 0) *s_nbad = 0;
-            __syncthreads();
-            if (bad) s_bad[atomicAdd(s_nbad, 1)] = tid;
-            __syncthreads();
-            const int nbad = *s_nbad;
-            for (int b = 0; b < nbad; ++b) {
-                const int     owner = s_bad[b];
-                const int64_t oli   = li0 + (int64_t)r * THREADS + owner;
-                const int64_t ogi   = P.i_global0 + oli;
-                const double2 p     = P.pos[ogi];
-                const double2 v     = P.vel[oli];
-                double fx, fy;
-                block_guarded_body(P.cm, ogi, half_drift(p.x, v.x, P.dt), half_drift(p.y, v.y, P.dt), s_red, fx, fy);
-                if (tid == owner) {
-                    sx[r] = fx;
-                    sy[r] = fy;
-                }
-            }
-            __syncthreads();
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int64_t li = li0 + (int64_t)r * THREADS + tid;
-        if (li < P.n_local) commit_body(P.cm, li, sx[r], sy[r]);
-    }
-    if (P.cm.px.enabled) {
-        // when this was the rank's last i-block, tell the peers
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();          // this CTA's stores to the peers, before the count
-            *s_nbad = (atomicAdd(P.cm.iblocks_done, 1) == P.cm.n_iblock - 1) ? 1 : 0;
-            if (*s_nbad) *P.cm.iblocks_done = 0;
-            __threadfence();
-        }
-        __syncthreads();
-        if (*s_nbad) publish_step(P.cm.px);
+        if (ring_row >= 0) P.clock.ring[ring_row * P.clock.npad + gi] = pn;
     }
 }
 
 // ---------------------------------------------------------------------------
-// K1: tiled pair accumulation (the hot kernel)
+// K1: tiled pair accumulation, all steps of a batch in one launch (the hot kernel)
 // ---------------------------------------------------------------------------
 //
-// ONE kernel per step: pair accumulation, reduction of the partial sums, the
-// guarded repair, kick + drift and -- sharded -- the hand-over of the new
-// positions to the peers all happen here.
-// Work = n_iblock x n_tile units (IB i-bodies against one j-tile).  The host
-// flattens the units i-block-major and gives each CTA an equal contiguous run
-// (a few Segments), so that one wave of SMs x ctas_per_sm CTAs finishes
+// Work of a step = n_iblock x n_tile units (IB i-bodies against one j-tile).  The
+// host flattens the units i-block-major and gives each CTA an equal contiguous
+// run (a few Segments), so that one wave of SMs x ctas_per_sm CTAs finishes
 // together whatever N is.  Each thread keeps R i-bodies (half-drifted position
-// + 2 accumulators) in registers; j-tiles arrive in a 4-deep shared-memory
-// ring filled by 1-D bulk copies issued by thread 0 and signalled through
-// mbarriers; every lane reads the same j, so the LDS are broadcasts.
+// + accumulators) in registers; j-tiles arrive in a 4-deep shared-memory ring
+// filled by 1-D bulk copies issued by thread 0 and signalled through mbarriers;
+// every lane reads the same j, so the LDS are broadcasts.
+//
+// The grid is launched cooperatively (every CTA resident) and runs ALL steps of
+// a gravity_cuda_step() batch.  There is no grid-wide barrier; the reference's
+// two spin barriers (sim_gravity.c:1140, :1226) become data-flow counters:
+//   arrivals[b]      partial rows of i-block b written (every CTA that holds a
+//                    segment of b adds one per step);
+//   commit           once all rows of b are there, EVERY CTA that contributed a
+//                    row commits its own 1/rows slice of b's bodies (sums the
+//                    rows in a fixed order, repairs poisoned bodies, kick +
+//                    drift, stores to self, peers and the PATH ring) -- the
+//                    reduction is spread over the CTAs instead of one straggler;
+//   iblock_ready[b]  set by the last slice to the step number b has reached; the
+//                    next step's segment of b and every fetch of a j-tile made of
+//                    b's bodies wait for it, nothing else does;
+//   peer flags       when the rank's last i-block of a step is committed the step
+//                    number goes to every peer; remote j-tiles wait for them.
+// Two position buffers suffice: i-block b can only be committed for step s+1 after
+// every tile of step s+1 was consumed, hence after every i-block (and every peer)
+// finished step s, hence after every CTA anywhere finished reading the buffer that
+// commit overwrites.
 
 template <int THREADS, int R, bool DIAG, bool FOLD>
 __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, const double *__restrict__ sm,
@@ -502,8 +504,133 @@ __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, con
     }
 }
 
+// Slice `k` of `rows` of i-block `iblock`: wait until every partial row of the
+// block has been written, add the rows up for this slice's bodies (lanes share a
+// body when the slice is narrower than the CTA; fixed order, run-to-run
+// deterministic), redo poisoned bodies on the guarded path, commit.  The last
+// slice of the block marks it ready for the next step; the last block of the
+// rank publishes the step to the peers.  Kept out of line so that it does not
+// disturb the register allocation of the pair loop.
+template <int THREADS, int R>
+__device__ __noinline__ void commit_slice(const TiledParams &P, const double2 *pos_cur, int nxt, int iblock, int row,
+                                          unsigned long long epoch, unsigned long long step_after, long long ring_row,
+                                          double *s_red, int *s_bad, int *s_nbad, volatile int *s_abort)
+{
+    constexpr int IB  = THREADS * R;
+    const int     tid = threadIdx.x;
+    const int     row0 = P.iblock_seg_begin[iblock];
+    const int     rows = P.iblock_seg_begin[iblock + 1] - row0;
+    const int     k    = row - row0;
+    const int     lo   = (int)(((long long)k * IB) / rows);
+    const int     hi   = (int)(((long long)(k + 1) * IB) / rows);
+    const int64_t li0  = (int64_t)iblock * IB;
+
+    if (tid == 0) {
+        if (!spin_until_reached<false>(P.arrivals + iblock, (unsigned long long)rows * (epoch + 1), P.wp,
+                                       kStatusLocalTimeout))
+            *s_abort = 1;
+    }
+    __syncthreads();
+    if (*s_abort) return;
+
+    // G lanes per body: the widest power of two that still covers the slice in one pass
+    int G = 1;
+    while (G < 32 && G * 2 * (hi - lo) <= THREADS && G * 2 <= rows) G <<= 1;
+    const int per_pass = THREADS / G;
+    const int g        = tid & (G - 1);
+    for (int base = lo; base < hi; base += per_pass) {
+        const int  bi    = base + tid / G;                 // body inside the i-block
+        const bool valid = bi < hi && li0 + bi < P.n_local;
+        double sxh = 0.0, sxl = 0.0, syh = 0.0, syl = 0.0;
+        if (valid) {
+            const double2 *ph = P.partial_hi + (size_t)row0 * IB + bi;
+            const double2 *pl = P.partial_lo + (size_t)row0 * IB + bi;
+            int r = g;
+            for (; r + 3 * G < rows; r += 4 * G) {          // four rows in flight
+                const double2 h0 = __ldcg(ph + (size_t)r * IB), h1 = __ldcg(ph + (size_t)(r + G) * IB);
+                const double2 h2 = __ldcg(ph + (size_t)(r + 2 * G) * IB), h3 = __ldcg(ph + (size_t)(r + 3 * G) * IB);
+                const double2 l0 = __ldcg(pl + (size_t)r * IB), l1 = __ldcg(pl + (size_t)(r + G) * IB);
+                const double2 l2 = __ldcg(pl + (size_t)(r + 2 * G) * IB), l3 = __ldcg(pl + (size_t)(r + 3 * G) * IB);
+                two_sum_acc(sxh, sxl, h0.x); two_sum_acc(syh, syl, h0.y); sxl += l0.x; syl += l0.y;
+                two_sum_acc(sxh, sxl, h1.x); two_sum_acc(syh, syl, h1.y); sxl += l1.x; syl += l1.y;
+                two_sum_acc(sxh, sxl, h2.x); two_sum_acc(syh, syl, h2.y); sxl += l2.x; syl += l2.y;
+                two_sum_acc(sxh, sxl, h3.x); two_sum_acc(syh, syl, h3.y); sxl += l3.x; syl += l3.y;
+            }
+            for (; r < rows; r += G) {
+                const double2 h0 = __ldcg(ph + (size_t)r * IB);
+                const double2 l0 = __ldcg(pl + (size_t)r * IB);
+                two_sum_acc(sxh, sxl, h0.x); two_sum_acc(syh, syl, h0.y); sxl += l0.x; syl += l0.y;
+            }
+        }
+        // combine the G lanes of a body: butterfly, both partners compute the same sum
+        for (int off = 1; off < G; off <<= 1) {
+            const double oxh = __shfl_xor_sync(0xffffffffu, sxh, off), oxl = __shfl_xor_sync(0xffffffffu, sxl, off);
+            const double oyh = __shfl_xor_sync(0xffffffffu, syh, off), oyl = __shfl_xor_sync(0xffffffffu, syl, off);
+            // order the operands by lane so that both partners round identically
+            if (g & off) {
+                double th = oxh, tl = oxl; two_sum_acc(th, tl, sxh); sxh = th; sxl = tl + sxl;
+                th = oyh; tl = oyl;        two_sum_acc(th, tl, syh); syh = th; syl = tl + syl;
+            } else {
+                two_sum_acc(sxh, sxl, oxh); sxl += oxl;
+                two_sum_acc(syh, syl, oyh); syl += oyl;
+            }
+        }
+        double sx = sxh + sxl, sy = syh + syl;
+        const bool owner = valid && g == 0;
+        const bool bad   = owner && !(isfinite(sx) && isfinite(sy));
+        if (__syncthreads_or(bad)) {
+            // poisoned bodies of this pass, one after the other, each by the whole CTA.
+            // Every position of this step is complete: all rows of the block have
+            // arrived, so every tile -- local and remote -- was fetched after its
+            // producer had published it.
+            if (tid == 0) *s_nbad = 0;
+            __syncthreads();
+            if (bad) s_bad[atomicAdd(s_nbad, 1)] = tid;
+            __syncthreads();
+            const int nbad = *s_nbad;
+            for (int b = 0; b < nbad; ++b) {
+                const int     owner_tid = s_bad[b];
+                const int64_t oli       = li0 + base + owner_tid / G;
+                const int64_t ogi       = P.i_global0 + oli;
+                const double2 p         = __ldcg(pos_cur + ogi);
+                const double2 v         = __ldcg(P.vel + oli);
+                double fx, fy;
+                block_guarded_body(pos_cur, P.mass, P.n, ogi, half_drift(p.x, v.x, P.dt), half_drift(p.y, v.y, P.dt),
+                                   s_red, fx, fy);
+                if (tid == owner_tid) {
+                    sx = fx;
+                    sy = fy;
+                }
+            }
+        }
+        if (owner) commit_body(P, pos_cur, nxt, li0 + bi, sx, sy, ring_row);
+    }
+
+    // ---- this slice is done; the last one hands the block (and the step) on ----
+    __syncthreads();
+    if (tid == 0) {
+        if (P.px.enabled && !P.export_accel) __threadfence_system();    // this CTA's stores to the peers
+        else __threadfence();
+        const unsigned long long slices = atomicAdd(P.slices_done + iblock, 1ull) + 1ull;
+        int last_block = 0;
+        if (slices == (unsigned long long)rows * (epoch + 1)) {
+            __threadfence();
+            if (!P.export_accel) st_release_gpu(P.iblock_ready + iblock, step_after);
+            const unsigned long long blocks = atomicAdd(P.iblocks_done, 1ull) + 1ull;
+            if (blocks == (unsigned long long)P.n_iblock * (epoch + 1)) {
+                last_block = 1;
+                if (P.px.enabled && !P.export_accel) __threadfence_system();
+            }
+        }
+        *s_nbad = last_block;
+    }
+    __syncthreads();
+    if (*s_nbad && P.px.enabled && !P.export_accel) publish_step(P.px, step_after);
+    __syncthreads();
+}
+
 template <int THREADS, int R, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumParams P)
+__global__ void __launch_bounds__(THREADS, MINB) k_tiled_steps(const TiledParams P)
 {
     constexpr int      IB         = THREADS * R;
     constexpr int      kWarps     = THREADS / 32;
@@ -515,13 +642,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
     __shared__ alignas(8) uint64_t  s_empty[kStages];
     __shared__ double               s_red[2 * THREADS];   // guarded path only
     __shared__ int                  s_bad[THREADS];
-    __shared__ int                  s_nbad, s_last;
+    __shared__ int                  s_nbad;
+    __shared__ volatile int         s_abort;
 
     const int tid  = threadIdx.x;
     const int lane = tid & 31;
 
     const int seg_begin = P.cta_seg_begin[blockIdx.x];
     const int seg_end   = P.cta_seg_begin[blockIdx.x + 1];
+    unsigned long long *trace = P.trace ? P.trace + (size_t)blockIdx.x * kTraceEvents : nullptr;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -529,123 +658,179 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_accumulate(const AccumP
             mbar_init(&s_empty[s], kWarps);
         }
         mbar_fence_init();
+        s_abort = 0;
+        if (trace) trace[0] = global_timer_ns();
     }
     __syncthreads();
 
-    // producer cursor (meaningful in thread 0 only)
-    int  p_seg = seg_begin, p_tile = 0, p_tile_end = 0, issued = 0;
-    bool peers_pending = P.wait_flags != nullptr;
-    if (tid == 0 && p_seg < seg_end) {
-        p_tile     = P.seg[p_seg].tile_begin;
-        p_tile_end = P.seg[p_seg].tile_end;
-    }
-    auto issue_next = [&]() {
-        if (p_seg >= seg_end) return;
-        const int stage = issued % kStages;
-        if (issued >= kStages) mbar_wait(&s_empty[stage], ((issued / kStages) - 1) & 1);
-        if (peers_pending && (p_tile < P.local_tile_begin || p_tile >= P.local_tile_end)) {
-            // first tile of other ranks' bodies: their stores of the previous step
-            // must have landed.  Tiles of this rank's own shard come first in every
-            // i-block's tile order, so the exchange hides behind them.
-            wait_for_peers_one_thread(P.wait_flags, P.wait_step, P.wait_rank, P.wait_nranks, P.wait_status);
-            peers_pending = false;
+    StepClock clk = P.clock;
+    int issued = 0, consumed = 0;            // tiles over the whole launch: the ring never restarts
+
+    for (long long step = 0; step < P.nsteps; ++step) {
+        const int cur = P.cur ^ (int)(step & 1);
+        const double2 *pos_cur = P.pos[cur];
+        const unsigned long long state_step = P.step_base + (unsigned long long)step;   // what pos_cur holds
+        const unsigned long long epoch      = P.epoch + (unsigned long long)step;
+        const long long ring_row = P.export_accel ? -1 : clock_tick(clk);
+
+        if (step > 0) {
+            // somebody gave up waiting: stop here, store nothing more
+            if (tid == 0 && *reinterpret_cast<volatile unsigned int *>(P.wp.status) != 0u) s_abort = 1;
+            __syncthreads();
         }
-        mbar_arrive_expect_tx(&s_full[stage], kTileBytes);
-        bulk_load(&s_pos[stage][0], P.pos + (size_t)p_tile * kTile, kTile * sizeof(double2), &s_full[stage]);
-        bulk_load(&s_mass[stage][0], P.mass + (size_t)p_tile * kTile, kTile * sizeof(double), &s_full[stage]);
-        ++issued;
-        if (++p_tile == p_tile_end) {
-            if (++p_seg < seg_end) {
-                p_tile     = P.seg[p_seg].tile_begin;
-                p_tile_end = P.seg[p_seg].tile_end;
+        if (s_abort) break;
+
+        // ---- producer cursor (meaningful in thread 0 only) ----
+        int  p_seg = seg_begin, p_tile = 0, p_tile_end = 0, p_ready_lo = 0, p_ready_hi = -1;
+        bool peers_pending = P.px.enabled != 0;
+        if (tid == 0 && p_seg < seg_end) {
+            p_tile     = P.seg[p_seg].tile_begin;
+            p_tile_end = P.seg[p_seg].tile_end;
+        }
+        auto issue_next = [&]() {
+            if (p_seg >= seg_end) return;
+            const int stage = issued % kStages;
+            if (issued >= kStages) mbar_wait(&s_empty[stage], ((issued / kStages) - 1) & 1);
+            if (p_tile >= P.local_tile_begin && p_tile < P.local_tile_end) {
+                if (step > 0) {
+                    // a tile of this device's own bodies: the i-blocks it is made of must have
+                    // been committed for this step
+                    const long long first = (long long)p_tile * kTile - P.i_global0;
+                    const int b_lo = (int)(first / IB);
+                    const int b_hi = min(P.n_iblock - 1, (int)((first + kTile - 1) / IB));
+                    for (int b = b_lo; b <= b_hi; ++b) {
+                        if (b >= p_ready_lo && b <= p_ready_hi) continue;
+                        if (!spin_until_reached<false>(P.iblock_ready + b, state_step, P.wp, kStatusLocalTimeout))
+                            s_abort = 1;
+                    }
+                    if (b_lo <= b_hi) { p_ready_lo = b_lo; p_ready_hi = b_hi; }
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
+            } else if (peers_pending) {
+                // first tile of other ranks' bodies in this step: their stores of the previous
+                // step must have landed.  Tiles of this rank's own shard come first in every
+                // CTA's tile order, so the exchange hides behind them.
+                if (!wait_for_peers_one_thread(P.px, state_step, P.wp)) s_abort = 1;
+                peers_pending = false;
             }
-        }
-    };
-    if (tid == 0) {
-        for (int k = 0; k < kLookahead; ++k) issue_next();
-    }
-
-    int consumed = 0;
-    for (int s = seg_begin; s < seg_end; ++s) {
-        const Segment sg = P.seg[s];
-        const int64_t li0 = (int64_t)sg.iblock * IB;     // first local i of the block
-
-        double  xi[R], yi[R], ax[R], ay[R];
-        int64_t gi[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int64_t li = li0 + (int64_t)r * THREADS + tid;
-            gi[r] = P.i_global0 + li;
-            ax[r] = 0.0;
-            ay[r] = 0.0;
-            if (li < P.n_local) {
-                const double2 p = P.pos[gi[r]];
-                const double2 v = P.vel[li];
-                xi[r] = half_drift(p.x, v.x, P.dt);      // sim_gravity.c:1186
-                yi[r] = half_drift(p.y, v.y, P.dt);      // sim_gravity.c:1187
-            } else {
-                xi[r] = 0.0;
-                yi[r] = 0.0;
-                gi[r] = -1;
+            mbar_arrive_expect_tx(&s_full[stage], kTileBytes);
+            bulk_load(&s_pos[stage][0], pos_cur + (size_t)p_tile * kTile, kTile * sizeof(double2), &s_full[stage]);
+            bulk_load(&s_mass[stage][0], P.mass + (size_t)p_tile * kTile, kTile * sizeof(double), &s_full[stage]);
+            ++issued;
+            if (++p_tile == p_tile_end) {
+                if (++p_seg < seg_end) {
+                    p_tile     = P.seg[p_seg].tile_begin;
+                    p_tile_end = P.seg[p_seg].tile_end;
+                }
             }
-        }
-        const int64_t gi_lo = P.i_global0 + li0;
-        const int64_t gi_hi = gi_lo + IB;
+        };
 
-        for (int t = sg.tile_begin; t < sg.tile_end; ++t) {
-            if (tid == 0) issue_next();
-            const double tile_m = P.tile_mass ? __ldg(P.tile_mass + t) : __longlong_as_double(0x7ff8000000000000LL);
-            const int stage = consumed % kStages;
-            mbar_wait(&s_full[stage], (consumed / kStages) & 1);
+        for (int s = seg_begin; s < seg_end; ++s) {
+            const Segment sg = P.seg[s];
+            const int64_t li0 = (int64_t)sg.iblock * IB;     // first local i of the block
 
-            const int64_t gj0  = (int64_t)t * kTile;
-            const bool    diag = gj0 < gi_hi && gj0 + kTile > gi_lo;
-            if (tile_m == tile_m) {
-                // all 256 masses of this tile are identical: sum without the mass,
-                // fold it in once per tile
-                double sx[R], sy[R];
+            if (step > 0) {
+                // the block's own bodies (and its partial rows) belong to the previous step
+                // until its last slice has been committed
+                if (tid == 0 && !spin_until_reached<false>(P.iblock_ready + sg.iblock, state_step, P.wp,
+                                                           kStatusLocalTimeout))
+                    s_abort = 1;
+                __syncthreads();
+            }
+            if (tid == 0 && s == seg_begin) {
+                for (int k = 0; k < kLookahead; ++k) issue_next();
+            }
+
+            double  xi[R], yi[R], ax[R], ay[R], cx[R], cy[R];
+            int64_t gi[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) sx[r] = sy[r] = 0.0;
-                if (diag) consume_tile<THREADS, R, true, true>(s_pos[stage], s_mass[stage], xi, yi, sx, sy, gi, gj0);
-                else      consume_tile<THREADS, R, false, true>(s_pos[stage], s_mass[stage], xi, yi, sx, sy, gi, gj0);
+            for (int r = 0; r < R; ++r) {
+                const int64_t li = li0 + (int64_t)r * THREADS + tid;
+                gi[r] = P.i_global0 + li;
+                ax[r] = ay[r] = cx[r] = cy[r] = 0.0;
+                if (li < P.n_local) {
+                    const double2 p = __ldcg(pos_cur + gi[r]);
+                    const double2 v = __ldcg(P.vel + li);
+                    xi[r] = half_drift(p.x, v.x, P.dt);      // sim_gravity.c:1186
+                    yi[r] = half_drift(p.y, v.y, P.dt);      // sim_gravity.c:1187
+                } else {
+                    xi[r] = 0.0;
+                    yi[r] = 0.0;
+                    gi[r] = -1;
+                }
+            }
+            const int64_t gi_lo = P.i_global0 + li0;
+            const int64_t gi_hi = gi_lo + IB;
+
+            for (int t = sg.tile_begin; t < sg.tile_end; ++t) {
+                if (tid == 0) issue_next();
+                const double tile_m = P.tile_mass ? __ldg(P.tile_mass + t) : __longlong_as_double(0x7ff8000000000000LL);
+                const int stage = consumed % kStages;
+                mbar_wait(&s_full[stage], (consumed / kStages) & 1);
+                if (trace && tid == 0 && consumed == 0) trace[1] = global_timer_ns();
+
+                const int64_t gj0  = (int64_t)t * kTile;
+                const bool    diag = gj0 < gi_hi && gj0 + kTile > gi_lo;
+                const bool    fold = tile_m == tile_m;
+                // every tile is summed into fresh registers and joins the running sum
+                // through a two-sum
+                double tx[R], ty[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) tx[r] = ty[r] = 0.0;
+                if (fold) {
+                    // all 256 masses of this tile are identical: sum without the mass,
+                    // fold it in once per tile
+                    if (diag) consume_tile<THREADS, R, true, true>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
+                    else      consume_tile<THREADS, R, false, true>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
+                } else if (diag) {
+                    consume_tile<THREADS, R, true, false>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
+                } else {
+                    consume_tile<THREADS, R, false, false>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[stage]);
+                ++consumed;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    ax[r] = fma(tile_m, sx[r], ax[r]);
-                    ay[r] = fma(tile_m, sy[r], ay[r]);
+                    two_sum_acc(ax[r], cx[r], fold ? tile_m * tx[r] : tx[r]);
+                    two_sum_acc(ay[r], cy[r], fold ? tile_m * ty[r] : ty[r]);
                 }
-            } else if (diag) {
-                consume_tile<THREADS, R, true, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
-            } else {
-                consume_tile<THREADS, R, false, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[stage]);
-            ++consumed;
-        }
 
-        double2 *out = P.partial + (size_t)sg.slot * IB;
+            double2 *out_hi = P.partial_hi + (size_t)sg.slot * IB;
+            double2 *out_lo = P.partial_lo + (size_t)sg.slot * IB;
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[r * THREADS + tid] = make_double2(ax[r], ay[r]);
-
-        // ---- the last CTA to finish a segment of this i-block commits it ----
-        // (the CTA barrier orders every thread's row before thread 0's fence and
-        // arrival; one fence per CTA instead of one per thread)
-        __syncthreads();
-        if (tid == 0) {
-            const int rows = P.cm.iblock_seg_begin[sg.iblock + 1] - P.cm.iblock_seg_begin[sg.iblock];
-            __threadfence();
-            s_last = (atomicAdd(P.cm.iblock_arrivals + sg.iblock, 1) == rows - 1) ? 1 : 0;
-            __threadfence();
+            for (int r = 0; r < R; ++r) {
+                const double hx = ax[r] + cx[r], hy = ay[r] + cy[r];
+                out_hi[r * THREADS + tid] = make_double2(hx, hy);
+                out_lo[r * THREADS + tid] = make_double2((ax[r] - hx) + cx[r], (ay[r] - hy) + cy[r]);
+            }
+            // one more row of this i-block is there (the CTA barrier orders every thread's
+            // row before thread 0's fence and arrival; one fence per CTA, not per thread)
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(P.arrivals + sg.iblock, 1ull);
+            }
         }
-        __syncthreads();
-        if (s_last) commit_iblock<THREADS, R>(P, sg.iblock, s_red, s_bad, &s_nbad);
+        if (trace && tid == 0 && step == 0) trace[2] = global_timer_ns();
+
+        // ---- commit duty: this CTA's slice of every i-block it contributed a row to ----
+        for (int s = seg_begin; s < seg_end; ++s) {
+            const Segment sg = P.seg[s];
+            commit_slice<THREADS, R>(P, pos_cur, cur ^ 1, sg.iblock, sg.slot, epoch, state_step + 1, ring_row, s_red,
+                                     s_bad, &s_nbad, &s_abort);
+            if (s_abort) break;
+        }
+        if (trace && tid == 0 && step == 0) trace[3] = global_timer_ns();
     }
+    if (trace && tid == 0) trace[4] = global_timer_ns();
 }
 
 // An empty shard still tells its peers that it has nothing to send.
-__global__ void k_publish_only(const PeerExchange X)
+__global__ void k_publish_only(const PeerExchange X, unsigned long long step)
 {
-    if (blockIdx.x == 0) publish_step(X);
+    if (blockIdx.x == 0) publish_step(X, step);
 }
 
 // ---------------------------------------------------------------------------
@@ -659,15 +844,22 @@ __global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitPara
 {
     __shared__ double2 s_pos[kStrictThreads];
     __shared__ double  s_mass[kStrictThreads];
+    __shared__ int     s_flag;
 
     const int64_t li     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool    active = li < P.n_local;
     const int64_t gi     = P.i_global0 + li;
     double px = 0.0, py = 0.0, sx = 0.0, sy = 0.0;
-    wait_for_peers(P.wait_flags, P.wait_step, P.px.rank, P.px.nranks, P.px.status);
+    if (P.px.enabled) {
+        // the peers' positions of this step must have landed before pos_cur is read
+        if (threadIdx.x == 0) s_flag = wait_for_peers_one_thread(P.px, P.wait_step, P.wp) ? 1 : 0;
+        __syncthreads();
+        if (!s_flag) return;                     // timed out: store nothing, publish nothing
+    }
+    double2 p = make_double2(0.0, 0.0), v = make_double2(0.0, 0.0);
     if (active) {
-        const double2 p = P.pos_cur[gi];
-        const double2 v = P.vel[li];
+        p  = P.pos_cur[gi];
+        v  = P.vel[li];
         px = half_drift(p.x, v.x, P.dt);
         py = half_drift(p.y, v.y, P.dt);
     }
@@ -687,15 +879,44 @@ __global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitPara
             }
         }
     }
-    if (active) commit_body(P, li, sx, sy);
-    if (!P.export_accel) publish_to_peers(P.px);
+    if (active) {
+        double nx, ny, nvx, nvy, ax, ay;
+        kick_drift(sx, P.dt, p.x, v.x, nx, nvx, ax);
+        kick_drift(sy, P.dt, p.y, v.y, ny, nvy, ay);
+        if (P.export_accel) {
+            P.accel_out[li] = make_double2(ax, ay);          // sim_gravity.c:1207-1208
+        } else {
+            const double2 pn = make_double2(nx, ny);
+            P.pos_next[gi] = pn;                             // NEXT_X, NEXT_Y  (:1218-1219)
+            P.vel[li]      = make_double2(nvx, nvy);         // NEXT_VX, NEXT_VY (:1220-1221)
+            if (P.px.enabled) {
+                for (int r = 0; r < P.px.nranks; ++r) {
+                    if (r != P.px.rank) P.px.peer_pos[P.cur_next][r][gi] = pn;
+                }
+            }
+            if (P.ring_row) P.ring_row[gi] = pn;             // PATH sample on a day change (:1248-1251)
+        }
+    }
+    if (P.px.enabled && !P.export_accel) {
+        // when the last CTA gets here all new positions of this rank are visible
+        // system-wide and the step number goes to every peer
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(P.commit_counter, 1u);
+            s_flag = (prev == gridDim.x - 1) ? 1 : 0;
+            if (s_flag) *P.commit_counter = 0u;              // ready for the next launch
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (s_flag) publish_step(P.px, P.publish_step);
+    }
 }
 
-// Stream-ordered wait for the peers' positions (download, energy): one warp.
-__global__ void k_wait_peers(const unsigned long long *flags, unsigned long long step, int rank, int nranks,
-                             unsigned int *status)
+// Stream-ordered wait for the peers' positions (download, energy, destroy): one thread.
+__global__ void k_wait_peers(const PeerExchange X, unsigned long long step, const WaitPolicy wp)
 {
-    wait_for_peers(flags, step, rank, nranks, status);
+    if (threadIdx.x == 0) wait_for_peers_one_thread(X, step, wp);
 }
 
 // N <= 1024, one device: the whole system lives in one CTA and `nsteps` steps
@@ -703,7 +924,7 @@ __global__ void k_wait_peers(const unsigned long long *flags, unsigned long long
 // two spin barriers, sim_gravity.c:1140 and :1226).
 __global__ void __launch_bounds__(kSmallMax) k_small_strict_steps(double2 *pos, double2 *vel,
                                                                   const double *mass, int n, double dt,
-                                                                  long long nsteps)
+                                                                  long long nsteps, StepClock clk)
 {
     __shared__ double2 s_pos[kSmallMax];
     __shared__ double  s_mass[kSmallMax];
@@ -731,6 +952,8 @@ __global__ void __launch_bounds__(kSmallMax) k_small_strict_steps(double2 *pos, 
             kick_drift(sx, dt, p.x, v.x, p.x, v.x, ax);
             kick_drift(sy, dt, p.y, v.y, p.y, v.y, ay);
         }
+        const long long ring_row = clock_tick(clk);          // commit block, sim_gravity.c:1232-1260
+        if (ring_row >= 0 && active) clk.ring[ring_row * clk.npad + i] = p;
         __syncthreads();
     }
     if (active) {
@@ -749,7 +972,8 @@ constexpr int kPairMax = 32;
 
 __global__ void __launch_bounds__(kPairMax * kPairMax) k_small_strict_steps_pairs(double2 *pos, double2 *vel,
                                                                                 const double *mass, int n,
-                                                                                double dt, long long nsteps)
+                                                                                double dt, long long nsteps,
+                                                                                StepClock clk)
 {
     __shared__ double2 s_pos[kPairMax];
     __shared__ double2 s_drift[kPairMax];
@@ -797,6 +1021,8 @@ __global__ void __launch_bounds__(kPairMax * kPairMax) k_small_strict_steps_pair
             double ax, ay;
             kick_drift(sx, dt, p.x, v.x, p.x, v.x, ax);
             kick_drift(sy, dt, p.y, v.y, p.y, v.y, ay);
+            const long long ring_row = clock_tick(clk);      // commit block, sim_gravity.c:1232-1260
+            if (ring_row >= 0) clk.ring[ring_row * clk.npad + i] = p;
         }
         // no third barrier: until the next one only owners touch shared memory,
         // each its own row, and only after it has finished reading it
@@ -824,6 +1050,7 @@ struct CoopParams {
     int           cur;
     double        dt;
     long long     nsteps;
+    StepClock     clock;
 };
 
 constexpr int kCoopThreads = 256;
@@ -860,6 +1087,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_strict_coop_steps(const CoopPa
     for (int j = tid; j < n; j += kCoopThreads) s_mass[j] = P.mass[j];
 
     int cur = P.cur;
+    StepClock clk = P.clock;
     for (long long s = 0; s < P.nsteps; ++s) {
         const double2 *src = P.pos[cur];
         for (int j = tid; j < n; j += kCoopThreads) s_pos[j] = src[j];
@@ -895,6 +1123,8 @@ __global__ void __launch_bounds__(kCoopThreads) k_strict_coop_steps(const CoopPa
             kick_drift(sy, P.dt, p.y, v.y, p.y, v.y, ay);
             P.pos[cur ^ 1][b0 + tid] = p;
         }
+        const long long ring_row = clock_tick(clk);          // commit block, sim_gravity.c:1232-1260
+        if (ring_row >= 0 && owner) clk.ring[ring_row * clk.npad + b0 + tid] = p;
         cur ^= 1;
         grid.sync();
     }

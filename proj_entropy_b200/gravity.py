@@ -55,6 +55,11 @@ def load_cuda_library():
         "gravity_cuda_accel": (C.c_int, [H, C.c_int32, _dp, _dp]),
         "gravity_cuda_step_objects": (C.c_int, [H, C.POINTER(C.c_void_p), C.c_int64, C.c_size_t, C.c_size_t,
                                                 C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_int64]),
+        "gravity_cuda_path_enable": (C.c_int, [H, C.c_int64]),
+        "gravity_cuda_step_path": (C.c_int, [H, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int32),
+                                             C.POINTER(C.c_int64)]),
+        "gravity_cuda_path_read": (C.c_int, [H, C.c_int64, C.c_int64, _dp, _dp]),
+        "gravity_cuda_trace_read": (C.c_int, [H, C.POINTER(C.c_uint64), C.c_int64, C.POINTER(C.c_int64)]),
         "gravity_cuda_energy": (C.c_int, [H, _dp, _dp]),
         "gravity_cuda_timer_start": (C.c_int, [H]),
         "gravity_cuda_timer_stop": (C.c_int, [H, _dp]),
@@ -189,13 +194,14 @@ class GravityCuda:
             self._check(self._lib.gravity_cuda_p2p_connect(self._h, buf, len(blobs)))
 
     def upload(self, mass, x, y, vx, vy):
+        """mass may be None after the first upload (the masses stay)."""
         n = self.n
-        arrs = [_f64(a, n) for a in (mass, x, y, vx, vy)]
-        self._check(self._lib.gravity_cuda_upload(self._h, *[_ptr(a) for a in arrs]))
+        arrs = [None if a is None else _f64(a, n) for a in (mass, x, y, vx, vy)]
+        self._check(self._lib.gravity_cuda_upload(self._h, *[None if a is None else _ptr(a) for a in arrs]))
 
     def upload_ptrs(self, mass, x, y, vx, vy):
-        """Raw host addresses (e.g. pinned torch tensors' data_ptr())."""
-        cast = lambda p: C.cast(C.c_void_p(int(p)), _dp)
+        """Raw host addresses (e.g. pinned torch tensors' data_ptr()); mass may be 0/None."""
+        cast = lambda p: C.cast(C.c_void_p(int(p)), _dp) if p else None
         self._check(self._lib.gravity_cuda_upload(self._h, cast(mass), cast(x), cast(y), cast(vx), cast(vy)))
 
     def download_ptrs(self, x, y, vx, vy):
@@ -203,7 +209,8 @@ class GravityCuda:
         self._check(self._lib.gravity_cuda_download(self._h, cast(x), cast(y), cast(vx), cast(vy)))
 
     def download(self):
-        out = [np.empty(self.n, dtype=np.float64) for _ in range(4)]
+        # zeros, not empty: with download_scope=1 only the caller's own shard is written
+        out = [np.zeros(self.n, dtype=np.float64) for _ in range(4)]
         self._check(self._lib.gravity_cuda_download(self._h, *[_ptr(a) for a in out]))
         return tuple(out)
 
@@ -216,9 +223,34 @@ class GravityCuda:
     def sync(self):
         self._check(self._lib.gravity_cuda_sync(self._h))
 
+    def path_enable(self, capacity):
+        self._check(self._lib.gravity_cuda_path_enable(self._h, int(capacity)))
+
+    def step_path(self, dt, nsteps, sim_time, last_day):
+        """-> (last_day after the batch, samples taken since path_enable)"""
+        ld, tail = C.c_int32(int(last_day)), C.c_int64()
+        self._check(self._lib.gravity_cuda_step_path(self._h, int(dt), int(nsteps), int(sim_time), C.byref(ld),
+                                                     C.byref(tail)))
+        return ld.value, tail.value
+
+    def path_read(self, first, count):
+        """-> (x, y), each [count, n]: PATH samples first..first+count-1 of every body"""
+        x = np.zeros((int(count), self.n), dtype=np.float64)
+        y = np.zeros((int(count), self.n), dtype=np.float64)
+        self._check(self._lib.gravity_cuda_path_read(self._h, int(first), int(count), _ptr(x), _ptr(y)))
+        return x, y
+
+    def trace_read(self, cap=2048):
+        """-> uint64 [n_cta, 8] globaltimer stamps of the last tiled launch (option trace=1)"""
+        buf = np.zeros((cap, 8), dtype=np.uint64)
+        n = C.c_int64()
+        self._check(self._lib.gravity_cuda_trace_read(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap,
+                                                      C.byref(n)))
+        return buf[:min(cap, n.value)]
+
     def accel(self, dt):
-        ax = np.empty(self.n, dtype=np.float64)
-        ay = np.empty(self.n, dtype=np.float64)
+        ax = np.zeros(self.n, dtype=np.float64)
+        ay = np.zeros(self.n, dtype=np.float64)
         self._check(self._lib.gravity_cuda_accel(self._h, int(dt), _ptr(ax), _ptr(ay)))
         return ax, ay
 

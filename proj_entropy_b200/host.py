@@ -42,6 +42,7 @@ def load_host_library():
         "gravity_scenario_load": (C.c_int, [C.c_char_p, C.POINTER(SP)]),
         "gravity_scenario_free": (None, [SP]),
         "gravity_scenario_save": (C.c_int, [SP, C.c_char_p]),
+        "gravity_scenario_save_error": (C.c_char_p, [C.c_int]),
         "gravity_plummer_generate": (C.c_int, [C.c_int64, C.c_uint64, _dp, _dp, _dp, _dp, _dp]),
         "gravity_steps_until_day_change": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
         "gravity_snapshot_write": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
@@ -85,8 +86,11 @@ class Scenario:
         cs.name = C.cast(names, C.POINTER(C.c_char * 32))
         cs.mass, cs.radius, cs.x, cs.y, cs.vx, cs.vy = [a.ctypes.data_as(_dp) for a in arrs]
         cs.disp_color, cs.max_path_disp_dflt = col.ctypes.data_as(_ip), pd.ctypes.data_as(_ip)
-        if lib.gravity_scenario_save(C.byref(cs), os.fsencode(pathname)) != 0:
+        rc = lib.gravity_scenario_save(C.byref(cs), os.fsencode(pathname))
+        if rc == -1:
             raise OSError("cannot write %s" % pathname)
+        if rc != 0:
+            raise ValueError("%s: %s" % (pathname, lib.gravity_scenario_save_error(rc).decode()))
 
 
 def load_scenario(pathname, inherit_dt=0, inherit_sim_width=0.0, max_objects=0):

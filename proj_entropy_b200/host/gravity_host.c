@@ -256,26 +256,95 @@ int gravity_scenario_load(const char *pathname, gravity_scenario_t **out)
     return gravity_scenario_load_ex(pathname, 0, 0.0, 0, out);
 }
 
+/* A NAME the reference's `sscanf("%s ...")` (sim_gravity.c:341-349) reads back as
+ * exactly one token and that its line classifier (:277-289) does not mistake for
+ * a comment or a PARAM line: white space and control characters become '_', an
+ * empty name becomes B<index>, a leading '#' and the bare word PARAM get a '_'
+ * in front.  An empty NAME would otherwise leave 8 fields behind a leading
+ * blank, i.e. "Invalid Object" -- and that blank would also count as one level of
+ * indentation (:358-368). */
+static void writable_name(const char *src, int index, char out[GRAVITY_MAX_NAME])
+{
+    char tmp[GRAVITY_MAX_NAME];
+    int i, len = 0, printable = 0;
+    for (i = 0; i < GRAVITY_MAX_NAME - 1 && src != NULL && src[i] != '\0'; i++) {
+        const unsigned char c = (unsigned char)src[i];
+        tmp[len++] = (c <= ' ' || c == 0x7f) ? '_' : (char)c;
+        if (c > ' ' && c != 0x7f) printable = 1;
+    }
+    tmp[len] = '\0';
+    if (!printable) {
+        snprintf(out, GRAVITY_MAX_NAME, "B%d", index);
+    } else if (tmp[0] == '#' || strcmp(tmp, "PARAM") == 0) {
+        snprintf(out, GRAVITY_MAX_NAME, "_%.*s", GRAVITY_MAX_NAME - 2, tmp);
+    } else {
+        snprintf(out, GRAVITY_MAX_NAME, "%s", tmp);
+    }
+}
+
+const char *gravity_scenario_save_error(int code)
+{
+    switch (code) {
+    case 0: return "ok";
+    case GRAVITY_SAVE_E_IO: return "cannot write the file";
+    case GRAVITY_SAVE_E_TOO_MANY: return "more than 200 bodies: the reference stops reading at MAX_OBJECT";
+    case GRAVITY_SAVE_E_DT: return "DT is not in the reference's table of step sizes and would be snapped on load";
+    case GRAVITY_SAVE_E_VALUE: return "a body field is not finite";
+    default: return "invalid argument";
+    }
+}
+
 int gravity_scenario_save(const gravity_scenario_t *s, const char *pathname)
 {
     FILE *fp;
-    int i;
-    if (s == NULL || pathname == NULL) return -1;
-    fp = fopen(pathname, "w");
-    if (fp == NULL) return -1;
-    fprintf(fp, "# %s -- written by libgravity_host at sim_time %lld s\n", s->sim_name,
-            (long long)s->sim_time);
-    fprintf(fp, "PARAM SIM_WIDTH %.17g AU\n", s->sim_width / GRAVITY_AU);
-    fprintf(fp, "PARAM DT_LINUX %d SEC\n", s->dt);
-    fprintf(fp, "PARAM DT_ANDROID %d SEC\n", s->dt);
-    for (i = 0; i < s->n; i++) {
-        int c = s->disp_color[i];
-        fprintf(fp, "%s %.17g %.17g %.17g %.17g %.17g %.17g %s %d\n", s->name[i], s->x[i], s->y[i],
-                s->vx[i], s->vy[i], s->mass[i], s->radius[i], k_colors[(c >= 0 && c < 10) ? c : 9],
-                s->max_path_disp_dflt[i]);
+    int i, wi, ok = 1;
+    if (s == NULL || pathname == NULL || s->n < 0) return GRAVITY_SAVE_E_ARG;
+    /* the reference silently stops at MAX_OBJECT bodies (:398-401): a longer file
+     * would load as a different system */
+    if (s->n > GRAVITY_MAX_OBJECT) return GRAVITY_SAVE_E_TOO_MANY;
+    /* DT is snapped down to valid_dt[] on load (:320-329); dt == 0 means "no PARAM
+     * line" (the loader's inherit value) and is written as no line at all */
+    if (s->dt != 0) {
+        for (i = 0; i < N_VALID_DT && k_valid_dt[i] != s->dt; i++) {}
+        if (i == N_VALID_DT) return GRAVITY_SAVE_E_DT;
     }
-    fclose(fp);
-    return 0;
+    for (i = 0; i < s->n; i++) {
+        if (!isfinite(s->x[i]) || !isfinite(s->y[i]) || !isfinite(s->vx[i]) || !isfinite(s->vy[i]) ||
+            !isfinite(s->mass[i]) || !isfinite(s->radius[i]))
+            return GRAVITY_SAVE_E_VALUE;
+    }
+    fp = fopen(pathname, "w");
+    if (fp == NULL) return GRAVITY_SAVE_E_IO;
+    ok &= fprintf(fp, "# %s -- written by libgravity_host at sim_time %lld s\n", s->sim_name,
+                  (long long)s->sim_time) > 0;
+    /* SIM_WIDTH is snapped DOWN to valid_sim_width[] on load (:299-311).  Writing
+     * sim_width/AU and multiplying by AU again can land one ulp below the table
+     * entry and fall to the next smaller one, so the table's own decimal literal
+     * is written instead: the reference then rebuilds the identical double. */
+    if (s->sim_width > 0) {
+        static const char *const lit[N_VALID_WIDTH] = {
+            ".01", ".02", ".05", ".1", ".2", ".5", "1", "2", "5", "10", "20", "50", "100", "200", "500", "1000",
+            "2000", "5000", "10000", "20000", "50000", "100000", "200000", "500000", "1000000", "2000000",
+            "5000000"};
+        for (wi = N_VALID_WIDTH - 1; wi > 0 && s->sim_width < valid_width(wi); wi--) {}
+        ok &= fprintf(fp, "PARAM SIM_WIDTH %s AU\n", lit[wi]) > 0;
+    }
+    if (s->dt != 0) {
+        ok &= fprintf(fp, "PARAM DT_LINUX %d SEC\n", s->dt) > 0;
+        ok &= fprintf(fp, "PARAM DT_ANDROID %d SEC\n", s->dt) > 0;
+    }
+    for (i = 0; i < s->n; i++) {
+        char name[GRAVITY_MAX_NAME];
+        int c = s->disp_color ? s->disp_color[i] : 9;
+        writable_name(s->name ? s->name[i] : NULL, i, name);
+        /* absolute coordinates, no indentation: relto[0] is all zero (:228), and
+         * %.17g round-trips every finite double through glibc's %lf */
+        ok &= fprintf(fp, "%s %.17g %.17g %.17g %.17g %.17g %.17g %s %d\n", name, s->x[i], s->y[i],
+                      s->vx[i], s->vy[i], s->mass[i], s->radius[i], k_colors[(c >= 0 && c < 10) ? c : 9],
+                      s->max_path_disp_dflt ? s->max_path_disp_dflt[i] : 0) > 0;
+    }
+    ok &= fclose(fp) == 0;
+    return ok ? 0 : GRAVITY_SAVE_E_IO;
 }
 
 /* ---- day sampling, sim_gravity.c:1232-1236 ---------------------------------- */

@@ -40,8 +40,12 @@ def test_abi_is_plain_c():
     out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "proj_entropy_b200", "libgravity_cuda.so")],
                          stdout=subprocess.PIPE, text=True).stdout
     exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
-    assert all(not s.startswith("_Z") or "gravity" not in s or True for s in exported)
-    assert set(declared_functions("gravity_cuda.h")) <= set(exported)
+    declared = set(declared_functions("gravity_cuda.h"))
+    assert declared <= set(exported)
+    # an entry point that lost its extern "C" would show up mangled (_Z...gravity_cuda_...)
+    assert [s for s in exported if s.startswith("_Z") and "gravity_cuda_" in s] == []
+    # and nothing unmangled is exported under the library's prefix without being in the header
+    assert {s for s in exported if s.startswith("gravity_")} == declared
 
 
 def test_no_cpu_fallback_without_gpu():
