@@ -25,7 +25,8 @@ $(PKG)/gravity_headless: $(PKG)/host/gravity_headless.c $(PKG)/libgravity_host.s
 	$(CC) $(HOSTFLAGS) -o $@ $(PKG)/host/gravity_headless.c -L$(PKG) -lgravity_host -lgravity_cuda \
 	    -Wl,-rpath,'$$ORIGIN' -lm
 
-oracle:
+# after the CUDA library: oracle/_ref/ref_gravity_gpu (the patched reference unit) links against it
+oracle: $(PKG)/libgravity_cuda.so
 	$(MAKE) -C oracle
 
 tools: tools/fp64_microbench tools/fp64_mix

@@ -14,7 +14,12 @@ One JSON line on stdout (rank 0):
   value     whole-job pairs/s with the state resident in HBM, K steps timed with
             CUDA events on the library's compute stream, max over ranks
   e2e       the same through the C ABI with HOST buffers: upload + step +
-            download per step, wall clock
+            download per step, wall clock; every rank moves only its own shard
+            over PCIe (40*N bytes in, 32*N bytes out per step in total)
+  parity    after the timed steps, outside the timed region: accelerations of the
+            state the run ended in, on a row sample, against the oracle (CPU
+            restatement of the reference loop) and against a long-double sum, and
+            whether every rank holds bit-identical results
   roofline  the step kernel (pairs + reduction + kick/drift in one launch) against the FP64 FMA pipe (20 flops per pair,
             north_star's convention); the peak is measured in this run by a DFMA
             microbenchmark because MEASURED_PEAKS.json has no FP64 entry
@@ -43,8 +48,17 @@ FP64_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 lanes x 2 x 1.965 GHz (BASELINE.md 
 # profiles/r1_ncu_full_k_tiled_accumulate_1m_final_raw.csv.  Algorithmic bytes are 72*N = 75.5 MB (positions,
 # masses, velocities read once: 40*N; new positions and velocities written: 32*N) plus the partial-sum rows.
 # Other configurations: not captured.
-NCU_DRAM_BYTES_PER_LAUNCH = {(1 << 20, 1): 48045824 + 33719040}
+NCU_DRAM_BYTES_PER_STEP = {(1 << 20, 1): 48045824 + 33719040}
 DT = 1
+SEED = 1
+
+
+def workload_config(n):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": "planar Plummer model N=%d, DT=%d s, seed %d (BASELINE.json configs[4] size at N=1048576)" % (n, DT, SEED),
+            "bodies": n, "dt_s": DT, "seed": SEED,
+            "l2": "compute-bound: 24*N bytes of j-state stream from L2/HBM per i-block, no flush needed; "
+                  "inputs change every step"}
 
 
 _REAL_STDOUT = None
@@ -90,6 +104,9 @@ def parse_args():
                     help="headline kernel path: 0 = general masses (13 FP64 instr/pair, default), 1 = let equal-mass "
                          "j-tiles take the 12-instruction path")
     ap.add_argument("--no-extra", action="store_true", help="skip the informational equal-mass-path measurement")
+    ap.add_argument("--persistent", type=int, default=1,
+                    help="1 = all timed steps in one launch of the step kernel (default), 0 = one launch per step")
+    ap.add_argument("--parity-rows", type=int, default=1024, help="rows of the in-run parity sample (0: skip)")
     return ap.parse_args()
 
 
@@ -169,7 +186,7 @@ def run_reference(args, rank):
     import proj_entropy_b200 as g
     n = args.bodies
     nthreads, ncpu = host_threads()
-    state = g.plummer(n, seed=1)
+    state = g.plummer(n, seed=SEED)
     rows = args.cpu_rows or auto_rows(n, nthreads, 12.0)
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_sample(state, max(nthreads, rows // 8), nthreads)
@@ -182,13 +199,17 @@ def run_reference(args, rank):
     all_cores = all_cores_sample(state, rows, ncpu) if ncpu != nthreads else None
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n * (n - 1) / value,
+        "steps": args.steps, "warmup": args.warmup,
+        # what was really timed: one bounded sample of the workload per step
+        "ms_per_step": 1e3 * t_total / args.steps,
+        "full_step_ms_extrapolated": 1e3 * n * (n - 1) / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "planar Plummer model N=%d, DT=1 s, seed 1" % n, "bodies": n,
-                   "step": "row-subsampled: %d i-rows x all %d j-bodies per timed step" % (rows, n)},
+        "config": workload_config(n),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
-                         "sample": "%d rows x %d bodies per step, %d steps; host has %d cpus; thread count is the "
-                                   "reference's policy min(nproc-1,16)" % (rows, n, args.steps, ncpu),
+                         "sample": "each timed step = %d of the %d i-rows x all %d j-bodies (the per-pair cost does not "
+                                   "depend on the row); %d steps; host has %d cpus; thread count is the reference's "
+                                   "policy min(nproc-1,16); oracle port, bit-identical to the unmodified reference TU"
+                                   % (rows, n, n, args.steps, ncpu),
                          "all_cores": all_cores, "reference_tu_small": reference_tu_sample()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -255,6 +276,47 @@ def measured_peaks():
         return {}
 
 
+def parity_record(h, g, ranks, state_mass, rows_wanted, rank, world):
+    """Outside the timed region: accelerations of the state the run ended in (sim_gravity.c:
+    1189-1208), on a row sample, against the oracle and against a long-double sum (rank 0),
+    plus whether every rank holds bit-identical positions, velocities and accelerations."""
+    import hashlib
+    import numpy as np
+    n = len(state_mass)
+    h.set_option("download_scope", 0)
+    x, y, vx, vy = h.download()                   # full arrays on every rank
+    ax, ay = h.accel(DT)                          # gathered from every rank
+    digest = hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in (x, y, vx, vy, ax, ay))).digest()
+    all_digests = ranks.all_gather_bytes(digest)
+    identical = all(all_digests[k * 32:(k + 1) * 32] == digest for k in range(world))
+    if rank != 0:
+        return None
+    from oracle import oracle_py as oracle
+    nthreads, _ = host_threads()
+    rows = np.unique(np.linspace(0, n - 1, max(512, rows_wanted)).astype(np.int64))
+    rax, ray = oracle.accel(state_mass, x, y, vx, vy, DT, rows=rows, nthreads=nthreads)
+    tax, tay = oracle.accel_ld(state_mass, x, y, vx, vy, DT, rows=rows, nthreads=nthreads)
+    mag, tmag = np.hypot(rax, ray), np.hypot(tax, tay)
+    err = np.hypot(ax[rows] - rax, ay[rows] - ray) / mag
+    floor = 0.1 * float(np.median(mag))
+    err_floor = np.hypot(ax[rows] - rax, ay[rows] - ray) / np.maximum(mag, floor)
+    gpu_ld = np.hypot(ax[rows] - tax, ay[rows] - tay) / tmag
+    ref_ld = np.hypot(rax - tax, ray - tay) / tmag
+    return {"rows": int(len(rows)), "state": "after the timed and end-to-end steps", "max_rel_vs_ref": float(err.max()),
+            "median_rel_vs_ref": float(np.median(err)), "n_above_1e-12": int((err > 1e-12).sum()),
+            "max_rel_vs_ref_with_floor": float(err_floor.max()), "floor_used": bool((err > 1e-12).any()),
+            "max_rel_vs_long_double": float(gpu_ld.max()), "ref_max_rel_vs_long_double": float(ref_ld.max()),
+            "median_rel_vs_long_double": float(np.median(gpu_ld)),
+            "ref_median_rel_vs_long_double": float(np.median(ref_ld)),
+            "rows_where_gpu_is_farther_from_long_double_than_ref": int((gpu_ld > ref_ld).sum()),
+            "ranks_bit_identical": bool(identical), "ranks_compared": world,
+            "gate": "per body |a - a_ref|_2 / |a_ref|_2 <= 1e-12 (BASELINE.json); tests/conftest.py:assert_accel_parity "
+                    "additionally tolerates, for at most 1 body in 10^4 whose net force nearly cancels, the same bound "
+                    "taken against max(|a_ref|, 0.1 median|a_ref|) if that body is no farther from a long-double sum "
+                    "than 4x the reference's own distance; floor_used says whether this sample needed it",
+            "pass": bool(err_floor.max() <= 1e-12 and (err > 1e-12).sum() <= max(1, len(rows) // 10000) and identical)}
+
+
 def run_ours(args, rank, world, local_rank):
     claim_stdout()
     import numpy as np
@@ -263,10 +325,10 @@ def run_ours(args, rank, world, local_rank):
 
     if g.device_count() < 1:
         raise SystemExit("bench.py: no sm_100 GPU visible; libgravity_cuda has no CPU fallback")
-    from proj_entropy_b200.dist import Ranks
+    from proj_entropy_b200.dist import Ranks, shard_bounds
     ranks = Ranks("nccl")
     n = args.bodies
-    state = g.plummer(n, seed=1)           # identical bytes on every rank
+    state = g.plummer(n, seed=SEED)        # identical bytes on every rank
     barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
 
     # the library's own NCCL communicator: id made on rank 0, broadcast by torch
@@ -274,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         nccl_id = ranks.broadcast_bytes(g.nccl_unique_id() if rank == 0 else None, 128)
 
-    opts = {"kernel": g.KERNEL_TILED, "mass_fold": args.mass_fold}
+    opts = {"kernel": g.KERNEL_TILED, "mass_fold": args.mass_fold, "persistent": args.persistent}
     if args.threads:
         opts["threads"] = args.threads
     if args.bodies_per_thread:
@@ -285,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
     exchange = 0
     if world > 1 and args.exchange == 1:
         # peer-memory exchange; if the peers cannot be mapped every rank stays on
-        # the NCCL all-gather (still GPU-to-GPU over NVLink; recorded in config)
+        # the NCCL all-gather (still GPU-to-GPU over NVLink; recorded in the line)
         try:
             h.p2p_connect(ranks.all_gather_bytes(h.p2p_export()))
             ok = 1.0
@@ -298,10 +360,9 @@ def run_ours(args, rank, world, local_rank):
 
     fp64_tf, fp64_mhz = g.fp64_peak(local_rank) if rank == 0 else (None, None)
 
-    # ---- device-resident throughput ------------------------------------------
+    # ---- device-resident throughput: K steps, one call ---------------------------
     h.upload(*state)
-    for _ in range(args.warmup):
-        h.step_async(DT, 1)
+    h.step_async(DT, args.warmup)
     h.sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -312,8 +373,7 @@ def run_ours(args, rank, world, local_rank):
     launches0 = h.launch_count()
     t0 = time.perf_counter()
     h.timer_start()
-    for _ in range(args.steps):
-        h.step_async(DT, 1)
+    h.step_async(DT, args.steps)
     ms = h.timer_stop()
     torch.cuda.synchronize()
     barrier()
@@ -326,10 +386,16 @@ def run_ours(args, rank, world, local_rank):
     pairs_per_step = float(n) * float(n - 1)
     value = pairs_per_step * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers -----------------------
+    # ---- end to end through the C ABI with host buffers ---------------------------
+    # every step: host -> device of that step's inputs, one step, device -> host of its
+    # result.  Each rank moves only its own shard over PCIe (upload reads nothing else,
+    # download_scope = 1 writes nothing else); the devices complete each other over NVLink.
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))     # bounded so that large --steps stay in minutes
+    lo, hi = shard_bounds(n, world, rank)
     pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
-    out = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(4)]
+    out = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(4)]
+    if world > 1:
+        h.set_option("download_scope", 1)
     h.upload_ptrs(*[t.data_ptr() for t in pinned])          # warm the path once
     h.step(DT, 1)
     h.download_ptrs(*[t.data_ptr() for t in out])
@@ -348,21 +414,23 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     te = max_over_ranks(time.perf_counter() - te0)
     e2e_value = pairs_per_step * e2e_steps / te
-    checksum = float(pinned[1].sum().item())
+    h2d_total = int(sum_over_ranks(float(5 * 8 * (hi - lo))))
+    d2h_total = int(sum_over_ranks(float(4 * 8 * (hi - lo))))
+
+    # ---- parity of the state this run ended in (not timed) ----------------------------
+    parity = parity_record(h, g, ranks, state[0], args.parity_rows, rank, world) if args.parity_rows > 0 else None
 
     # ---- informational: the equal-mass fast path on the same workload ----------
     extra = None
     if not args.no_extra and not args.mass_fold:
         h.set_option("mass_fold", 1)
         h.upload(*state)
-        for _ in range(min(2, args.warmup)):
-            h.step_async(DT, 1)
+        h.step_async(DT, min(2, args.warmup))
         h.sync()
         barrier()
         h.timer_start()
         fold_steps = max(1, min(args.steps, 5))
-        for _ in range(fold_steps):
-            h.step_async(DT, 1)
+        h.step_async(DT, fold_steps)
         ms_fold = max_over_ranks(h.timer_stop())
         barrier()
         extra = {"value": pairs_per_step * fold_steps / (ms_fold * 1e-3), "unit": UNIT,
@@ -383,37 +451,40 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peaks = measured_peaks()
-        per_launch_pairs = pairs_per_step / world            # every rank runs 1/world of the pairs per step
         n_hot = max(1, kernel_launches)
         avg_kernel_ms = kernel_ms / n_hot
-        launches_per_step = max(1, round(kernel_launches / args.steps))
-        achieved = FLOPS_PER_PAIR * per_launch_pairs / launches_per_step / (avg_kernel_ms * 1e-3) / 1e12
+        steps_per_launch = args.steps / n_hot
+        per_launch_pairs = pairs_per_step / world * steps_per_launch     # every rank runs 1/world of the pairs of a step
+        achieved = FLOPS_PER_PAIR * per_launch_pairs / (avg_kernel_ms * 1e-3) / 1e12
+        dram = NCU_DRAM_BYTES_PER_STEP.get((n, world))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "planar Plummer model N=%d, DT=1 s, seed 1 (BASELINE.json configs[4] size)" % n,
-                       "bodies": n, "parallelism": "i-sharded x%d, %s" % (world, "peer-memory stores of the new positions from the step "
+            "config": workload_config(n),
+            "variant": {"parallelism": "i-sharded x%d, %s" % (world, "peer-memory stores of the new positions from the step "
                                        "kernel + step flags" if exchange == 1 else
                                        "NCCL all-gather of positions per step"),
-                       "l2": "compute-bound: 24*N bytes of j-state stream from L2/HBM per i-block, no flush needed; "
-                             "inputs change every step",
-                       "kernel": "tiled rsqrt, general masses, 13 FP64-pipe instr/pair" if not args.mass_fold else
-                                 "tiled rsqrt, equal-mass tiles folded, 12 FP64-pipe instr/pair",
-                       "mass_fold": args.mass_fold, "exchange": exchange},
+                        "kernel": "tiled rsqrt, general masses, 13 FP64-pipe instr/pair" if not args.mass_fold else
+                                  "tiled rsqrt, equal-mass tiles folded, 12 FP64-pipe instr/pair",
+                        "mass_fold": args.mass_fold, "exchange": exchange, "persistent": args.persistent,
+                        "steps_per_launch": steps_per_launch},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 5 * 8 * n * world,
-                    "d2h_bytes_per_step": 4 * 8 * n * world, "steps": e2e_steps, "checksum_x": checksum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
+                    "d2h_bytes_per_step": d2h_total, "steps": e2e_steps,
+                    "note": "sum over ranks: every rank copies only its own shard (40 and 32 bytes per body)"},
             "gpu_launches": total_launches,
+            "parity": parity,
             "roofline": {"bound": "fp64_fma_pipe", "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
                          "frac": achieved / fp64_tf if fp64_tf else None,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((n, world)),
+                         "traffic": dram * steps_per_launch if dram else None,
+                         "traffic_note": "ncu dram bytes of a one-step launch x steps per launch",
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry: "
                                         "keys %s)" % sorted(peaks.keys())[:4],
                          "peak_sm_mhz": fp64_mhz, "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
                          "flops_per_pair": FLOPS_PER_PAIR, "reference_fp64_ops_per_pair": 13,
                          "sass_fp64_instr_per_pair": 12 if args.mass_fold else 13, "sass_mufu_per_pair": 1,
-                         "kernel": "k_tiled_accumulate",
+                         "kernel": "k_tiled_steps",
                          "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kernel_launches,
                          "kernel_share_of_step": kernel_ms / ms if ms else None,
                          "job_frac_of_nominal": FLOPS_PER_PAIR * value / 1e12 / (FP64_NOMINAL_TFLOPS * world)},

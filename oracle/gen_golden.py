@@ -37,6 +37,7 @@ REFERENCE_SCENARIOS = {
     "solar_system_and_rogue_star": BASE_STEPS + [k * 10000 for k in range(2, 11)],
 }
 AUTHORED_STEPS = [0, 1, 2, 3, 10, 100, 1000]
+AUTHORED_STEPS_LONG = {"solar_system_daily": [0, 1, 2, 3, 10, 100, 1000, 10000]}
 
 
 def run(path, steps):
@@ -62,11 +63,31 @@ def fixture(name, path, steps, source):
         "radius": [b["radius"] for b in first["bodies"]],
         "checkpoints": [
             {"steps": l["steps"], "sim_time": l["sim_time"],
+             # PATH ring of the commit block (sim_gravity.c:1248-1260): samples taken so far and
+             # their digest (oracle/ref_harness/path_digest.h)
+             "path_tail": l["path_tail"], "path_hash": l["path_hash"],
              "x": [b["x"] for b in l["bodies"]], "y": [b["y"] for b in l["bodies"]],
              "vx": [b["vx"] for b in l["bodies"]], "vy": [b["vy"] for b in l["bodies"]]}
             for l in lines],
     })
     return fx
+
+
+def author_solar_system_daily(path):
+    """The parsed solar-system state (tests/golden/ref_solar_system.json, 13 bodies) written
+    back in the reference's format by libgravity_host with DT = 1 day: every commit is a day
+    change, the case the device-side PATH ring exists for."""
+    sys.path.insert(0, ROOT)
+    from proj_entropy_b200 import host
+    import numpy as np
+    fx = json.load(open(os.path.join(OUT, "ref_solar_system.json")))
+    cp = fx["checkpoints"][0]
+    f = lambda key, src=cp: np.array([float.fromhex(v) for v in src[key]])
+    n = fx["n"]
+    sc = host.Scenario("SOLAR_SYSTEM_DAILY", 86400, float.fromhex(fx["sim_width"]), fx["names"], f("mass", fx),
+                       f("radius", fx), f("x"), f("y"), f("vx"), f("vy"), np.full(n, 9, np.int32),
+                       np.full(n, 400, np.int32))
+    sc.save(path)
 
 
 def main():
@@ -80,8 +101,10 @@ def main():
         json.dump(fx, open(os.path.join(OUT, "ref_%s.json" % name), "w"), indent=1)
         print("ref_%s.json" % name, fx.get("n"), fx.get("dt"))
     sdir = os.path.join(OUT, "scenarios")
+    author_solar_system_daily(os.path.join(sdir, "solar_system_daily"))
     for name in sorted(os.listdir(sdir)):
-        fx = fixture(name, os.path.join(sdir, name), AUTHORED_STEPS, "authored:tests/golden/scenarios/" + name)
+        fx = fixture(name, os.path.join(sdir, name), AUTHORED_STEPS_LONG.get(name, AUTHORED_STEPS),
+                     "authored:tests/golden/scenarios/" + name)
         fx["sim_gravity_c_md5"] = src_md5
         json.dump(fx, open(os.path.join(OUT, "own_%s.json" % name), "w"), indent=1)
         print("own_%s.json" % name, fx.get("n"), fx.get("dt"), fx.get("error"))

@@ -19,7 +19,8 @@
  *     decides step by step whether the workers RUN, STOP or TERMINATE.
  *   - to read a consistent state we request STATE_STOP for one round: worker
  *     0 reaches that barrier only after its commit (sim_gravity.c:1238-1255).
- * Works for N <= MAX_THREAD-1 = 15 bodies, which covers all six scenarios.
+ * Works for N <= MAX_THREAD-1 = 15 bodies, which covers all six scenarios; a run
+ * that only asks for step 0 (the parsed initial state) works for any N.
  *
  * usage: ref_gravity <scenario> <steps> [<steps> ...]   (ascending, cumulative)
  * output: one JSON object per requested step count, one per line.
@@ -29,11 +30,15 @@
 #undef pthread_create
 extern int pthread_create(pthread_t *, const pthread_attr_t *, void *(*)(void *), void *);
 
+#include "path_digest.h"
+
 static void dump(FILE *out, const char *path, long long steps)
 {
     int i;
-    fprintf(out, "{\"scenario\": \"%s\", \"steps\": %lld, \"sim_time\": %lld, \"dt\": %d, \"n\": %d, \"sim_width\": \"%a\", \"bodies\": [",
-            path, steps, (long long)sim.sim_time, DT, sim.max_object, sim_width);
+    fprintf(out, "{\"scenario\": \"%s\", \"steps\": %lld, \"sim_time\": %lld, \"dt\": %d, \"n\": %d, \"sim_width\": \"%a\", "
+                 "\"path_tail\": %lld, \"path_hash\": \"%016llx\", \"bodies\": [",
+            path, steps, (long long)sim.sim_time, DT, sim.max_object, sim_width, (long long)path_tail,
+            (unsigned long long)reference_path_digest());
     for (i = 0; i < sim.max_object; i++) {
         object_t *o = sim.object[i];
         fprintf(out, "%s{\"name\": \"%s\", \"mass\": \"%a\", \"radius\": \"%a\", \"x\": \"%a\", \"y\": \"%a\", \"vx\": \"%a\", \"vy\": \"%a\"}",
@@ -59,6 +64,12 @@ int main(int argc, char **argv)
         return 1;
     }
     n = sim.max_object;
+    if (atoll(argv[argc - 1]) == 0) {
+        /* parse only (every requested step count is 0): no workers needed, so any N the
+         * reference's parser accepts (up to MAX_OBJECT) can be dumped */
+        for (a = 2; a < argc; a++) dump(stdout, argv[1], 0);
+        return 0;
+    }
     if (n + 1 > MAX_THREAD) {
         fprintf(stderr, "ref_harness: N=%d exceeds MAX_THREAD-1\n", n);
         return 3;

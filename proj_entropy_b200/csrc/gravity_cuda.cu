@@ -173,29 +173,36 @@ int effective_kernel(const gravity_cuda_t *h)
 
 typedef void (*accum_kernel_t)(const TiledParams);
 
-template <int T, int R>
+template <int T, int R, bool F>
 accum_kernel_t accum_for_minb(int minb)
 {
     switch (minb) {
-    case 1: return k_tiled_steps<T, R, 1>;
-    case 2: return k_tiled_steps<T, R, 2>;
-    case 3: return k_tiled_steps<T, R, 3>;
-    default: return k_tiled_steps<T, R, 4>;
+    case 1: return k_tiled_steps<T, R, 1, F>;
+    case 2: return k_tiled_steps<T, R, 2, F>;
+    case 3: return k_tiled_steps<T, R, 3, F>;
+    default: return k_tiled_steps<T, R, 4, F>;
     }
 }
 
-accum_kernel_t pick_accum(int threads, int bpt, int minb)
+template <bool F>
+accum_kernel_t pick_accum_f(int threads, int bpt, int minb)
 {
     if (threads == 128) {
-        if (bpt == 1) return accum_for_minb<128, 1>(minb);
-        if (bpt == 2) return accum_for_minb<128, 2>(minb);
-        if (bpt == 4) return accum_for_minb<128, 4>(minb);
+        if (bpt == 1) return accum_for_minb<128, 1, F>(minb);
+        if (bpt == 2) return accum_for_minb<128, 2, F>(minb);
+        if (bpt == 4) return accum_for_minb<128, 4, F>(minb);
     } else if (threads == 256) {
-        if (bpt == 1) return accum_for_minb<256, 1>(minb);
-        if (bpt == 2) return accum_for_minb<256, 2>(minb);
-        if (bpt == 4) return accum_for_minb<256, 4>(minb);
+        if (bpt == 1) return accum_for_minb<256, 1, F>(minb);
+        if (bpt == 2) return accum_for_minb<256, 2, F>(minb);
+        if (bpt == 4) return accum_for_minb<256, 4, F>(minb);
     }
     return nullptr;
+}
+
+// foldable: the kernel variant that tests every j-tile for a common mass (option mass_fold)
+accum_kernel_t pick_accum(int threads, int bpt, int minb, bool foldable = true)
+{
+    return foldable ? pick_accum_f<true>(threads, bpt, minb) : pick_accum_f<false>(threads, bpt, minb);
 }
 
 // ---- launch plan -------------------------------------------------------------
@@ -363,7 +370,7 @@ int build_plan_impl(gravity_cuda_t *h)
         const int n_tile = (int)((h->n + kTile - 1) / kTile);
         int threads = 0, bpt = 0, ctas = 0;
         choose_shape(c.n_local, n_tile, c.num_sms, h->opt_threads, h->opt_bpt, h->opt_ctas_per_sm, threads, bpt, ctas);
-        accum_kernel_t probe = pick_accum(threads, bpt, ctas);
+        accum_kernel_t probe = pick_accum(threads, bpt, ctas, h->opt_mass_fold != 0);
         if (!probe) return fail(h, "unsupported tiled kernel shape threads=%d bodies_per_thread=%d", threads, bpt);
         int occ = 0;
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe, threads, 0));
@@ -553,7 +560,7 @@ int launch_tiled(gravity_cuda_t *h, DeviceCtx &c, double dt, long long nsteps, b
     P.clock = clk;
     P.wp = wait_policy(h, c);
     P.px = peer_exchange(h, c, p2p_active(h));
-    accum_kernel_t k = pick_accum(c.threads, c.bpt, c.minb);
+    accum_kernel_t k = pick_accum(c.threads, c.bpt, c.minb, P.tile_mass != nullptr);
     void *args[] = {&P};
     hot_event(h, c);
     // cooperative: every CTA is resident, which the in-kernel waits between CTAs rely on

@@ -20,7 +20,11 @@
 namespace gravity {
 
 constexpr int    kTile        = 256;     // j-bodies per shared-memory tile
-constexpr int    kPairsPerIteration = 16;
+#ifndef GRAVITY_PAIRS_GENERAL_R4
+#define GRAVITY_PAIRS_GENERAL_R4 32
+#endif
+constexpr int    kPairsPerIteration = 16;           // pairs per unrolled iteration of the pair loop ...
+constexpr int    kPairsPerIterationGeneralR4 = GRAVITY_PAIRS_GENERAL_R4;   // ... and of its general-mass, 4-bodies-per-thread form
 constexpr int    kStages      = 4;       // tile ring depth
 constexpr int    kLookahead   = 2;       // tiles in flight ahead of the consumer
 constexpr int    kSmallMax    = 1024;    // largest N of the single-CTA kernel
@@ -482,8 +486,9 @@ __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, con
                                              double (&ax)[R], double (&ay)[R],
                                              const int64_t (&gi)[R], int64_t gj0)
 {
-    // 16 pairs per unrolled iteration whatever R is (measured best for R = 2 and 4)
-    constexpr int kUnroll = kPairsPerIteration / R;
+    // pairs per unrolled iteration, measured (profiles/r2_unroll_ab.log): 16 whatever R is, except the
+    // general-mass loop of the 4-bodies-per-thread shape, which schedules best with 32
+    constexpr int kUnroll = ((!FOLD && R == 4) ? kPairsPerIterationGeneralR4 : kPairsPerIteration) / R;
 #pragma unroll kUnroll
     for (int j = 0; j < kTile; ++j) {
         const double2 pj = sp[j];
@@ -629,8 +634,20 @@ __device__ __noinline__ void commit_slice(const TiledParams &P, const double2 *p
     __syncthreads();
 }
 
-template <int THREADS, int R, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_tiled_steps(const TiledParams P)
+#ifndef GRAVITY_TILE_TWOSUM
+#define GRAVITY_TILE_TWOSUM 1      // developer switch: 0 = general-mass tiles accumulate straight into the running sum
+#endif
+#ifdef GRAVITY_MAXNREG
+#define GRAVITY_KERNEL_BOUNDS(T, M) __maxnreg__(GRAVITY_MAXNREG)
+#else
+#define GRAVITY_KERNEL_BOUNDS(T, M) __launch_bounds__(T, M)
+#endif
+
+// FOLDABLE = false compiles the equal-mass tile path out (option mass_fold = 0, or no
+// tile of the system qualifies): the general-mass pair loop then gets the register
+// allocation to itself.
+template <int THREADS, int R, int MINB, bool FOLDABLE>
+__global__ void GRAVITY_KERNEL_BOUNDS(THREADS, MINB) k_tiled_steps(const TiledParams P)
 {
     constexpr int      IB         = THREADS * R;
     constexpr int      kWarps     = THREADS / 32;
@@ -764,14 +781,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_steps(const TiledParams
 
             for (int t = sg.tile_begin; t < sg.tile_end; ++t) {
                 if (tid == 0) issue_next();
-                const double tile_m = P.tile_mass ? __ldg(P.tile_mass + t) : __longlong_as_double(0x7ff8000000000000LL);
+                const double tile_m = FOLDABLE ? __ldg(P.tile_mass + t) : __longlong_as_double(0x7ff8000000000000LL);
                 const int stage = consumed % kStages;
                 mbar_wait(&s_full[stage], (consumed / kStages) & 1);
                 if (trace && tid == 0 && consumed == 0) trace[1] = global_timer_ns();
 
                 const int64_t gj0  = (int64_t)t * kTile;
                 const bool    diag = gj0 < gi_hi && gj0 + kTile > gi_lo;
-                const bool    fold = tile_m == tile_m;
+                const bool    fold = FOLDABLE && tile_m == tile_m;
                 // every tile is summed into fresh registers and joins the running sum
                 // through a two-sum
                 double tx[R], ty[R];
@@ -782,11 +799,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k_tiled_steps(const TiledParams
                     // fold it in once per tile
                     if (diag) consume_tile<THREADS, R, true, true>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
                     else      consume_tile<THREADS, R, false, true>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
+#if GRAVITY_TILE_TWOSUM
                 } else if (diag) {
                     consume_tile<THREADS, R, true, false>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
                 } else {
                     consume_tile<THREADS, R, false, false>(s_pos[stage], s_mass[stage], xi, yi, tx, ty, gi, gj0);
                 }
+#else
+                } else if (diag) {
+                    consume_tile<THREADS, R, true, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
+                } else {
+                    consume_tile<THREADS, R, false, false>(s_pos[stage], s_mass[stage], xi, yi, ax, ay, gi, gj0);
+                }
+#endif
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[stage]);
                 ++consumed;

@@ -3,18 +3,21 @@
  *
  * This is the reference's worker loop (sim_gravity_thread,
  * sim_gravity.c:1130-1273) with the display split off: the body of
- * `if (local_state == STATE_RUN)` is one gravity_cuda_step() call, and what
+ * `if (local_state == STATE_RUN)` is one call into libgravity_cuda, and what
  * the reference keeps around it stays here in host C -- the simulation clock
- * (sim_time += DT, :1255), the once-per-day PATH ring sampling (:1232-1236,
- * :1248-1251, :1258-1260) and the RATE Y/S readout (:912-919).  Steps are
- * batched up to the next day boundary so that the PATH samples are taken at
- * exactly the commits at which the reference takes them.
+ * (sim_time += DT, :1255), the PATH rings (:1248-1251, :1258-1260) and the RATE
+ * Y/S readout (:912-919).  The PATH samples themselves are taken ON THE DEVICE
+ * (gravity_cuda_step_path): the step kernels carry the commit block's day test
+ * (:1232-1236), so a batch of any length -- also at DT = 1 day, where every commit
+ * is a sample -- is one call, and the host fetches the new samples once per batch.
  *
  * usage: gravity_headless (--scenario FILE | --plummer N [--seed S] | --resume SNAPSHOT)
  *            [--steps K] [--dt SECONDS] [--gpus P] [--kernel auto|tiled|strict]
- *            [--checkpoint K1,K2,...] [--save SNAPSHOT] [--no-path] [--quiet]
+ *            [--checkpoint K1,K2,...] [--save SNAPSHOT] [--save-scenario FILE]
+ *            [--path-batch ROWS] [--no-path] [--quiet]
  * prints one JSON line per checkpoint (body state as C99 hex floats) and a
- * final timing line.
+ * final timing line.  --save-scenario writes the final state in the reference's
+ * own scenario format (at most 200 bodies), readable by the original app.
  */
 #include "gravity_cuda.h"
 #include "gravity_host.h"
@@ -49,12 +52,32 @@ static void dump_state(const char *label, long long steps, const gravity_scenari
     fflush(stdout);
 }
 
+/* Digest of the PATH rings, samples in order, bodies in index order, X then Y, each
+ * double folded as a 64-bit word FNV-1a style -- the value the reference harness
+ * prints for the reference's own rings (tests compare the two). */
+static uint64_t path_digest(const path_point_t *path, int n, long long tail)
+{
+    uint64_t h = 14695981039346656037ULL;
+    long long k, first = tail > MAX_PATH_SAMPLES ? tail - MAX_PATH_SAMPLES : 0;
+    int i;
+    if (path == NULL) return h;
+    for (k = first; k < tail; k++) {
+        for (i = 0; i < n; i++) {
+            uint64_t w[2];
+            memcpy(w, &path[(size_t)i * MAX_PATH_SAMPLES + (size_t)(k % MAX_PATH_SAMPLES)], sizeof(w));
+            h = (h ^ w[0]) * 1099511628211ULL;
+            h = (h ^ w[1]) * 1099511628211ULL;
+        }
+    }
+    return h;
+}
+
 static int usage(const char *argv0)
 {
     fprintf(stderr,
             "usage: %s (--scenario FILE | --plummer N [--seed S] | --resume SNAPSHOT) [--steps K] [--dt SEC]\n"
             "          [--gpus P] [--kernel auto|tiled|strict] [--checkpoint K1,K2,...] [--save SNAPSHOT]\n"
-            "          [--no-path] [--quiet]\n",
+            "          [--save-scenario FILE] [--path-batch ROWS] [--no-path] [--quiet]\n",
             argv0);
     return 2;
 }
@@ -62,7 +85,9 @@ static int usage(const char *argv0)
 int main(int argc, char **argv)
 {
     const char *scenario_file = NULL, *checkpoints = NULL, *kernel = "auto", *resume_file = NULL, *save_file = NULL;
-    long long plummer_n = 0, steps = 1000, seed = 1, done = 0, next_cp;
+    const char *save_scenario_file = NULL;
+    long long plummer_n = 0, steps = 1000, seed = 1, done = 0, next_cp, path_batch = 4096, path_reads = 0;
+    double *ring_x = NULL, *ring_y = NULL;
     int dt_override = 0, gpus = 1, quiet = 0, want_path = 1, a, i;
     gravity_scenario_t *sim = NULL;
     gravity_cuda_t *h = NULL;
@@ -83,6 +108,8 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--checkpoint") && a + 1 < argc) checkpoints = argv[++a];
         else if (!strcmp(argv[a], "--resume") && a + 1 < argc) resume_file = argv[++a];
         else if (!strcmp(argv[a], "--save") && a + 1 < argc) save_file = argv[++a];
+        else if (!strcmp(argv[a], "--save-scenario") && a + 1 < argc) save_scenario_file = argv[++a];
+        else if (!strcmp(argv[a], "--path-batch") && a + 1 < argc) path_batch = atoll(argv[++a]);
         else if (!strcmp(argv[a], "--no-path")) want_path = 0;
         else if (!strcmp(argv[a], "--quiet")) quiet = 1;
         else return usage(argv[0]);
@@ -146,6 +173,11 @@ int main(int argc, char **argv)
             fprintf(stderr, "ERROR plummer generator failed\n");
             return 1;
         }
+        for (i = 0; i < sim->n; i++) {      /* display-only fields, for --save-scenario */
+            sim->radius[i] = 1.0E6;
+            sim->disp_color[i] = 9;
+            sim->max_path_disp_dflt[i] = 30;
+        }
     }
     if (dt_override > 0) sim->dt = dt_override;
 
@@ -165,8 +197,16 @@ int main(int argc, char **argv)
         fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
         return 1;
     }
-    if (want_path && sim->n <= GRAVITY_MAX_OBJECT) {
+    if (want_path && sim->n <= GRAVITY_MAX_OBJECT && sim->dt >= 1 && sim->sim_time >= 0) {
+        if (path_batch < 3) path_batch = 3;
+        if (path_batch > MAX_PATH_SAMPLES) path_batch = MAX_PATH_SAMPLES;
         path = calloc((size_t)sim->n * MAX_PATH_SAMPLES, sizeof(path_point_t));
+        ring_x = malloc(sizeof(double) * (size_t)path_batch * (size_t)sim->n);
+        ring_y = malloc(sizeof(double) * (size_t)path_batch * (size_t)sim->n);
+        if (!path || !ring_x || !ring_y || gravity_cuda_path_enable(h, path_batch) != 0) {
+            fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+            return 1;
+        }
     }
 
     if (checkpoints) cp_cursor = strdup(checkpoints);
@@ -185,31 +225,45 @@ int main(int argc, char **argv)
     t0 = microsec_now();
     while (done < steps) {
         long long batch = steps - done;
-        long long to_sample = gravity_steps_until_day_change(sim->sim_time, sim->dt, last_day);
-        int sample = 0;
-        if (path && to_sample <= batch) {
-            batch = to_sample;
-            sample = 1;
-        }
-        if (next_cp > done && next_cp - done < batch) {
-            batch = next_cp - done;
-            sample = 0;
-        }
-        if (gravity_cuda_step(h, sim->dt, batch) != 0) {
-            fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
-            return 1;
-        }
-        /* commit bookkeeping of thread 0 (sim_gravity.c:1229-1260) for the batch */
-        if (sample) {
-            if (gravity_cuda_download(h, sim->x, sim->y, NULL, NULL) != 0) return 1;
-            for (i = 0; i < sim->n; i++) {
-                path[(size_t)i * MAX_PATH_SAMPLES + path_tail % MAX_PATH_SAMPLES].x = sim->x[i];
-                path[(size_t)i * MAX_PATH_SAMPLES + path_tail % MAX_PATH_SAMPLES].y = sim->y[i];
+        if (next_cp > done && next_cp - done < batch) batch = next_cp - done;
+        if (path) {
+            /* no more samples per batch than the device ring has rows: k steps take at most
+             * k samples, and at most k*dt/86400 + 2 */
+            long long cap_steps = path_batch;
+            if (sim->dt < 86400) cap_steps = (path_batch - 2) * (86400 / sim->dt);
+            long long tail_after = 0;
+            long long k;
+            if (batch > cap_steps) batch = cap_steps;
+            if (gravity_cuda_step_path(h, sim->dt, batch, sim->sim_time, &last_day, (int64_t *)&tail_after) != 0) {
+                fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+                return 1;
             }
+            /* the commit block's PATH writes (sim_gravity.c:1248-1251, :1258-1260), fetched once per batch */
+            if (tail_after > path_tail) {
+                const long long cnt = tail_after - path_tail;
+                if (gravity_cuda_path_read(h, path_tail, cnt, ring_x, ring_y) != 0) {
+                    fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+                    return 1;
+                }
+                path_reads++;
+                for (k = 0; k < cnt; k++) {
+                    const size_t slot = (size_t)((path_tail + k) % MAX_PATH_SAMPLES);
+                    for (i = 0; i < sim->n; i++) {
+                        path[(size_t)i * MAX_PATH_SAMPLES + slot].x = ring_x[(size_t)k * sim->n + i];
+                        path[(size_t)i * MAX_PATH_SAMPLES + slot].y = ring_y[(size_t)k * sim->n + i];
+                    }
+                }
+                path_tail = tail_after;
+            }
+        } else {
+            if (gravity_cuda_step(h, sim->dt, batch) != 0) {
+                fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+                return 1;
+            }
+            /* the day test still runs at every commit (sim_gravity.c:1234-1236): what it leaves behind */
             last_day = (int32_t)((sim->sim_time + (batch - 1) * (long long)sim->dt) / 86400);
-            path_tail++;
         }
-        sim->sim_time += (long long)sim->dt * batch;
+        sim->sim_time += (long long)sim->dt * batch;            /* :1255 */
         done += batch;
         if (done == next_cp) {
             char *tok;
@@ -229,6 +283,15 @@ int main(int argc, char **argv)
             return 1;
         }
     }
+    if (save_scenario_file) {
+        int rc;
+        if (gravity_cuda_download(h, sim->x, sim->y, sim->vx, sim->vy) != 0) return 1;
+        rc = gravity_scenario_save(sim, save_scenario_file);
+        if (rc != 0) {
+            fprintf(stderr, "ERROR cannot write scenario '%s': %s\n", save_scenario_file, gravity_scenario_save_error(rc));
+            return 1;
+        }
+    }
     if (!quiet) {
         double secs = (double)(t1 - t0) / 1e6;
         double kin = 0, pot = 0;
@@ -236,15 +299,20 @@ int main(int argc, char **argv)
         gravity_cuda_energy(h, &kin, &pot);
         gravity_cuda_launch_count(h, (int64_t *)&launches);
         printf("{\"summary\": \"%s\", \"n\": %d, \"steps\": %lld, \"dt\": %d, \"gpus\": %d, \"wall_s\": %.6f, "
-               "\"pairs_per_s\": %.6g, \"rate_years_per_s\": %.6g, \"path_samples\": %lld, "
+               "\"pairs_per_s\": %.6g, \"rate_years_per_s\": %.6g, \"path_samples\": %lld, \"path_hash\": \"%016llx\", "
+               "\"path_reads\": %lld, \"sim_time\": %lld, \"last_day\": %d, "
                "\"kinetic\": \"%a\", \"potential\": \"%a\", \"kernel_launches\": %lld}\n",
                sim->sim_name, sim->n, done, sim->dt, gpus, secs,
                secs > 0 ? (double)sim->n * (sim->n - 1) * (double)done / secs : 0.0,
-               secs > 0 ? (double)sim->dt * (double)done / YEAR_SECS / secs : 0.0, path_tail, kin, pot, launches);
+               secs > 0 ? (double)sim->dt * (double)done / YEAR_SECS / secs : 0.0, path_tail,
+               (unsigned long long)path_digest(path, sim->n, path_tail), path_reads, (long long)sim->sim_time, last_day,
+               kin, pot, launches);
     }
 
     gravity_cuda_destroy(h);
     free(path);
+    free(ring_x);
+    free(ring_y);
     free(cp_cursor);
     gravity_scenario_free(sim);
     return 0;

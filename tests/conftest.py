@@ -105,3 +105,36 @@ def assert_accel_parity(ax, ay, rax, ray, state=None, dt=None, tol=1e-12):
         e_ref = np.hypot(rax[out] - tax, ray[out] - tay) / t
         assert (e_gpu <= 4 * e_ref + 1e-15).all(), (e_gpu, e_ref)
     return pure
+
+
+def scenario_from_fixture(fx):
+    """A proj_entropy_b200.Scenario holding the fixture's parsed initial state."""
+    import proj_entropy_b200 as g
+    cp = fx["checkpoints"][0]
+    n = fx["n"]
+    return g.Scenario(fx["scenario"].upper(), fx["dt"], float.fromhex(fx["sim_width"]), list(fx["names"]),
+                      fx["mass_f"], hexarr(fx["radius"]), cp["x_f"], cp["y_f"], cp["vx_f"], cp["vy_f"],
+                      np.full(n, 9, np.int32), np.full(n, 30, np.int32))
+
+
+def scenario_file_for(fx, tmp_path):
+    """A scenario file the REFERENCE's parser turns into the fixture's initial state:
+    the authored file itself, or -- the reference's own files are not in this
+    repository and not on the GPU box -- the fixture's parsed state written back
+    out by gravity_scenario_save (absolute coordinates, no indentation)."""
+    kind, rel = fx["source"].split(":", 1)
+    if kind == "authored":
+        return os.path.join(ROOT, rel)
+    out = os.path.join(str(tmp_path), fx["scenario"])
+    scenario_from_fixture(fx).save(out)
+    return out
+
+
+def path_digest(xs, ys):
+    """Digest of PATH samples xs, ys [samples, n] as oracle/ref_harness/path_digest.h
+    computes it for the reference's rings."""
+    h = 14695981039346656037
+    words = np.stack([np.asarray(xs, np.float64), np.asarray(ys, np.float64)], axis=-1).reshape(-1).view(np.uint64)
+    for w in words.tolist():
+        h = ((h ^ w) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h

@@ -430,7 +430,8 @@ def test_headless_c_driver_matches_reference_bits(name):
         for key in ("x", "y", "vx", "vy"):
             got = [float.fromhex(b[key]) for b in s["bodies"]]
             assert bits_equal(got, cp[key + "_f"]), "%s step %d %s" % (name, s["steps"], key)
-    assert summary["path_samples"] == _reference_path_samples(steps[-1], fx["dt"])
+    assert summary["path_samples"] == _reference_path_samples(steps[-1], fx["dt"]) == fx["checkpoints"][-1]["path_tail"]
+    assert summary["path_hash"] == fx["checkpoints"][-1]["path_hash"]     # the reference's own PATH rings
 
 
 def test_upload_download_round_trip_bits():
