@@ -43,12 +43,13 @@ METRIC = "fp64 pair-interactions/s"
 UNIT = "pairs/s"
 FLOPS_PER_PAIR = 20            # BASELINE.json north_star convention
 FP64_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 lanes x 2 x 1.965 GHz
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_tiled_accumulate<256,4,1> launch (= one whole step) at
+# dram__bytes_read.sum + dram__bytes_write.sum of a one-step launch of k_tiled_steps<256,4,1,false> at
 # the default workload (N = 1,048,576 on one GPU), from the `ncu --set full` capture summarised in
-# profiles/r1_ncu_full_k_tiled_accumulate_1m_final_raw.csv.  Algorithmic bytes are 72*N = 75.5 MB (positions,
-# masses, velocities read once: 40*N; new positions and velocities written: 32*N) plus the partial-sum rows.
+# profiles/r2_ncu_full_k_tiled_steps_1m_raw.csv.  Algorithmic bytes are 72*N = 75.5 MB (positions,
+# masses, velocities read once: 40*N; new positions and velocities written: 32*N) plus the partial-sum rows
+# (written and read once each, hi + lo: 64 bytes per body and segment, ~1,170 segments of 1,024 bodies at this size).
 # Other configurations: not captured.
-NCU_DRAM_BYTES_PER_STEP = {(1 << 20, 1): 48045824 + 33719040}
+NCU_DRAM_BYTES_PER_STEP = {(1 << 20, 1): 71849216 + 57456128}
 DT = 1
 SEED = 1
 
@@ -107,6 +108,9 @@ def parse_args():
     ap.add_argument("--persistent", type=int, default=1,
                     help="1 = all timed steps in one launch of the step kernel (default), 0 = one launch per step")
     ap.add_argument("--parity-rows", type=int, default=1024, help="rows of the in-run parity sample (0: skip)")
+    ap.add_argument("--spin-timeout-ms", type=int, default=-1,
+                    help="library option spin_timeout_ms (-1: library default, 10 s; 0: wait for ever -- use under "
+                         "ncu --set full, whose instrumented passes slow the kernel far beyond any sane limit)")
     return ap.parse_args()
 
 
@@ -337,6 +341,8 @@ def run_ours(args, rank, world, local_rank):
         nccl_id = ranks.broadcast_bytes(g.nccl_unique_id() if rank == 0 else None, 128)
 
     opts = {"kernel": g.KERNEL_TILED, "mass_fold": args.mass_fold, "persistent": args.persistent}
+    if args.spin_timeout_ms >= 0:
+        opts["spin_timeout_ms"] = args.spin_timeout_ms
     if args.threads:
         opts["threads"] = args.threads
     if args.bodies_per_thread:

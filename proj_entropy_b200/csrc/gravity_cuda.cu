@@ -44,6 +44,7 @@ struct DeviceCtx {
     unsigned long long *flags = nullptr;           // [kMaxPeers], written by the peers
     unsigned int       *commit_counter = nullptr;
     unsigned int       *status = nullptr;          // kStatus*: != 0 makes the handle fail-stop
+    unsigned int       *host_status = nullptr;     // mapped host copy of the verdict (read without a memcpy)
     double2            *peer_pos[2][kMaxPeers] = {};
     unsigned long long *peer_flags[kMaxPeers] = {};
     bool                ipc_opened[kMaxPeers] = {};
@@ -457,6 +458,7 @@ WaitPolicy wait_policy(const gravity_cuda_t *h, const DeviceCtx &c)
 {
     WaitPolicy wp;
     wp.status = c.status;
+    wp.host_status = c.host_status;
     wp.timeout_cycles = h->opt_spin_timeout_ms > 0 ? (long long)h->opt_spin_timeout_ms * c.clock_khz : 0;
     return wp;
 }
@@ -657,9 +659,8 @@ int enqueue_wait_peers(gravity_cuda_t *h, DeviceCtx &c)
 int check_status(gravity_cuda_t *h)
 {
     for (DeviceCtx &c : h->ctx) {
-        unsigned int st = 0;
-        CUDA_TRY(h, cudaSetDevice(c.device));
-        CUDA_TRY(h, cudaMemcpy(&st, c.status, sizeof(st), cudaMemcpyDeviceToHost));
+        // written by the kernel that gave up, before it ended; every caller synchronised the stream first
+        const unsigned int st = c.host_status ? *reinterpret_cast<volatile unsigned int *>(c.host_status) : 0u;
         if (st != 0) {
             h->dead = true;
             return fail(h, st == kStatusPeerTimeout
@@ -717,6 +718,8 @@ int init_ctx(gravity_cuda_t *h, DeviceCtx &c)
     CUDA_TRY(h, cudaMalloc(&c.flags, sizeof(unsigned long long) * kMaxPeers));
     CUDA_TRY(h, cudaMalloc(&c.commit_counter, sizeof(unsigned int)));
     CUDA_TRY(h, cudaMalloc(&c.status, sizeof(unsigned int)));
+    CUDA_TRY(h, cudaHostAlloc(&c.host_status, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *c.host_status = 0u;
     CUDA_TRY(h, cudaMemsetAsync(c.flags, 0, sizeof(unsigned long long) * kMaxPeers, c.stream));
     CUDA_TRY(h, cudaMemsetAsync(c.commit_counter, 0, sizeof(unsigned int), c.stream));
     CUDA_TRY(h, cudaMemsetAsync(c.status, 0, sizeof(unsigned int), c.stream));
@@ -888,6 +891,7 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         if (c.ev_stop) cudaEventDestroy(c.ev_stop);
         if (c.ev_copy) cudaEventDestroy(c.ev_copy);
+        if (c.host_status) cudaFreeHost(c.host_status);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
     delete h;

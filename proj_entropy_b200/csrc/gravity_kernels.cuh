@@ -96,7 +96,8 @@ struct Segment {
 
 // Spin-wait policy shared by every kernel that waits on another CTA or GPU.
 struct WaitPolicy {
-    unsigned int *status;          // device word, see kStatus*
+    unsigned int *status;          // device word, see kStatus*: what the kernels poll
+    unsigned int *host_status;     // the same verdict in mapped host memory: what the host reads, without a copy
     long long     timeout_cycles;  // 0: wait for ever
 };
 
@@ -258,7 +259,10 @@ __device__ __forceinline__ bool spin_until_reached(const unsigned long long *p, 
         if ((++polls & 63u) == 0u) {
             if (*reinterpret_cast<volatile unsigned int *>(wp.status) != 0u) return false;
             if (wp.timeout_cycles > 0 && clock64() - t0 > wp.timeout_cycles) {
-                atomicCAS(wp.status, 0u, code);
+                if (atomicCAS(wp.status, 0u, code) == 0u && wp.host_status != nullptr) {
+                    *reinterpret_cast<volatile unsigned int *>(wp.host_status) = code;
+                    __threadfence_system();
+                }
                 return false;
             }
         }
