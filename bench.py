@@ -321,7 +321,9 @@ def parity_record(h, g, ranks, state_mass, rows_wanted, rank, world):
             "pass": bool(err_floor.max() <= 1e-12 and (err > 1e-12).sum() <= max(1, len(rows) // 10000) and identical)}
 
 
-def run_ours(args, rank, world, local_rank):
+def run_ours(args, rank, world, local_rank, ranks=None):
+    """ranks: an open proj_entropy_b200.dist.Ranks to reuse (tools/matrix.py runs several cells in
+    one process); by default one is opened here and closed at the end."""
     claim_stdout()
     import numpy as np
     import torch
@@ -330,7 +332,9 @@ def run_ours(args, rank, world, local_rank):
     if g.device_count() < 1:
         raise SystemExit("bench.py: no sm_100 GPU visible; libgravity_cuda has no CPU fallback")
     from proj_entropy_b200.dist import Ranks, shard_bounds
-    ranks = Ranks("nccl")
+    own_ranks = ranks is None
+    if own_ranks:
+        ranks = Ranks("nccl")
     n = args.bodies
     state = g.plummer(n, seed=SEED)        # identical bytes on every rank
     barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
@@ -502,7 +506,10 @@ def run_ours(args, rank, world, local_rank):
         emit(line)
     sampler.stop()
     h.close()
-    ranks.close()
+    if own_ranks:
+        ranks.close()
+    else:
+        ranks.barrier()
 
 
 def main():

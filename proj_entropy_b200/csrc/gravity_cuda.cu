@@ -99,6 +99,7 @@ struct gravity_cuda {
     bool dead = false;               // a device-side wait gave up: fail-stop
     unsigned long long step_id = 0;  // steps committed since create (absolute step number of the state)
     unsigned long long epoch = 0;    // evaluations done with the current plan of the tiled kernel
+    unsigned long long xfer_steps = 0;   // of those, committed steps that stored to the peers
     int64_t path_capacity = 0;       // rows of the PATH ring (0: off)
     int64_t path_tail = 0;           // samples taken since path_enable
     int64_t launches = 0;
@@ -399,7 +400,7 @@ int build_plan_impl(gravity_cuda_t *h)
         cudaFree(c.partial_lo); cudaFree(c.counters); cudaFree(c.trace);
         c.seg = nullptr; c.cta_seg_begin = nullptr; c.iblock_seg_begin = nullptr; c.partial_hi = nullptr;
         c.partial_lo = nullptr; c.counters = nullptr; c.trace = nullptr;
-        // arrivals[n_iblock] | slices_done[n_iblock] | iblock_ready[n_iblock] | iblocks_done[1]: monotonic,
+        // arrivals[n_iblock] | slices_done[n_iblock] | iblock_ready[n_iblock] | xfer_done[1]: monotonic,
         // zeroed here together with h->epoch (iblock_ready compares against absolute step numbers and
         // is only consulted for steps after the first of a launch, so 0 is a valid start)
         const size_t n_counters = (size_t)3 * std::max(1, c.n_iblock) + 1;
@@ -422,6 +423,7 @@ int build_plan_impl(gravity_cuda_t *h)
                                cudaMemcpyHostToDevice));
     }
     h->epoch = 0;
+    h->xfer_steps = 0;
     h->planned = true;
     return 0;
 }
@@ -546,7 +548,9 @@ int launch_tiled(gravity_cuda_t *h, DeviceCtx &c, double dt, long long nsteps, b
     P.arrivals = c.counters;
     P.slices_done = c.counters + nb;
     P.iblock_ready = c.counters + 2 * nb;
-    P.iblocks_done = c.counters + 3 * nb;
+    P.xfer_done = c.counters + 3 * nb;
+    P.xfer_base = (unsigned long long)c.n_seg * h->xfer_steps;
+    P.n_seg_total = c.n_seg;
     P.trace = c.trace;
     P.epoch = h->epoch;
     P.step_base = h->step_id;
@@ -620,7 +624,10 @@ int enqueue_steps(gravity_cuda_t *h, double dt, long long nsteps, bool export_ac
                 CUDA_TRY(h, cudaGetLastError());
             }
         }
-        if (kernel == GRAVITY_CUDA_KERNEL_TILED) h->epoch += (unsigned long long)chunk;
+        if (kernel == GRAVITY_CUDA_KERNEL_TILED) {
+            h->epoch += (unsigned long long)chunk;
+            if (p2p && !export_accel) h->xfer_steps += (unsigned long long)chunk;
+        }
         if (!export_accel) {
             for (long long k = 0; k < chunk; ++k) clock_tick(host_clk);
             if (gather) {
@@ -1035,6 +1042,19 @@ int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value)
     return 0;
 }
 
+// The device-side alias of a page-locked host array (cudaHostAlloc / cudaHostRegister, e.g. a
+// pinned torch tensor), or NULL for ordinary pageable memory.
+static double *pinned_alias(const double *p)
+{
+    if (p == nullptr) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? static_cast<double *>(a.devicePointer) : nullptr;
+}
+
 int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, const double *y,
                         const double *vx, const double *vy)
 {
@@ -1048,9 +1068,25 @@ int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, 
     // position and mass arrays with one in-place all-gather over NVLink.  That
     // collective also orders this upload after every peer's earlier step kernels,
     // which may still be storing into this device's buffers.
+    // page-locked host arrays are read in place by one kernel per device; pageable ones go
+    // through staging copies
+    const double *px = pinned_alias(x), *py = pinned_alias(y), *pvx = pinned_alias(vx), *pvy = pinned_alias(vy);
+    const double *pm = pinned_alias(mass);
+    const bool in_place = px && py && pvx && pvy && (pm || !mass);
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
         double *sx = c.stage, *sy = c.stage + np, *svx = c.stage + 2 * np, *svy = c.stage + 3 * np;
+        if (in_place) {
+            if (c.n_local > 0) {
+                k_upload_shard_pinned<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(
+                    px + c.i0, py + c.i0, pvx + c.i0, pvy + c.i0, pm ? pm + c.i0 : nullptr, c.pos[0] + c.i0, c.vel,
+                    c.mass + c.i0, c.n_local);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+            }
+            CUDA_TRY(h, cudaEventRecord(c.ev_copy, c.stream));      // the host arrays are free again after this
+            continue;
+        }
         if (c.n_local > 0) {
             const size_t bytes = sizeof(double) * c.n_local;
             CUDA_TRY(h, cudaMemcpyAsync(sx, x + c.i0, bytes, cudaMemcpyHostToDevice, c.stream));
@@ -1144,6 +1180,23 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
     // a handle that holds every shard itself, or a caller that asked for its own shard
     // only ("download_scope" = 1), needs no exchange: every device returns what it owns
     const bool own_only = h->single_process || h->nranks == 1 || h->opt_download_scope == 1;
+    if (own_only) {
+        // page-locked destinations are written in place by one kernel per device
+        double *px = pinned_alias(x), *py = pinned_alias(y), *pvx = pinned_alias(vx), *pvy = pinned_alias(vy);
+        if ((px || !x) && (py || !y) && (pvx || !vx) && (pvy || !vy)) {
+            for (DeviceCtx &c : h->ctx) {
+                if (c.n_local == 0) continue;
+                CUDA_TRY(h, cudaSetDevice(c.device));
+                k_download_shard_pinned<<<(unsigned)((c.n_local + 255) / 256), 256, 0, c.stream>>>(
+                    c.pos[h->cur] + c.i0, c.vel, px ? px + c.i0 : nullptr, py ? py + c.i0 : nullptr,
+                    pvx ? pvx + c.i0 : nullptr, pvy ? pvy + c.i0 : nullptr, c.n_local);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+            }
+            if (sync_all(h) != 0) return -1;
+            return check_status(h);
+        }
+    }
     if (x || y) {
         if (own_only) {
             if (download_shards(h, src_pos, true, x, y, 0) != 0) return -1;

@@ -23,7 +23,11 @@ constexpr int    kTile        = 256;     // j-bodies per shared-memory tile
 #ifndef GRAVITY_PAIRS_GENERAL_R4
 #define GRAVITY_PAIRS_GENERAL_R4 32
 #endif
+#ifndef GRAVITY_PAIRS_FOLD_R4
+#define GRAVITY_PAIRS_FOLD_R4 32
+#endif
 constexpr int    kPairsPerIteration = 16;           // pairs per unrolled iteration of the pair loop ...
+constexpr int    kPairsPerIterationFoldR4 = GRAVITY_PAIRS_FOLD_R4;
 constexpr int    kPairsPerIterationGeneralR4 = GRAVITY_PAIRS_GENERAL_R4;   // ... and of its general-mass, 4-bodies-per-thread form
 constexpr int    kStages      = 4;       // tile ring depth
 constexpr int    kLookahead   = 2;       // tiles in flight ahead of the consumer
@@ -139,7 +143,10 @@ struct TiledParams {
     unsigned long long *arrivals;       // [n_iblock] partial rows written, all evaluations
     unsigned long long *slices_done;    // [n_iblock] slices committed, all evaluations
     unsigned long long *iblock_ready;   // [n_iblock] absolute step number this i-block has reached
-    unsigned long long *iblocks_done;   // [1] i-blocks committed, all evaluations
+    unsigned long long *xfer_done;      // [1] slices whose stores to the peers are visible system-wide (committed steps only)
+    unsigned long long  xfer_base;      // value of *xfer_done before this launch
+    int32_t             n_seg_total;    // segments (= slices) of one step on this device
+    int32_t             reserved2;
     unsigned long long *trace;          // [gridDim.x][kTraceEvents] globaltimer stamps, or NULL
     unsigned long long  epoch;          // evaluations done with this plan before this launch
     unsigned long long  step_base;      // absolute step number of the state at launch
@@ -270,16 +277,45 @@ __device__ __forceinline__ bool spin_until_reached(const unsigned long long *p, 
     }
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // One thread: every peer has published `step`, i.e. its positions of that step
-// have landed in this device's buffer.  The tiles are then fetched by the async
-// proxy (bulk copies), hence the proxy fence.
+// have landed in this device's buffer.  All flags are polled together (the loads
+// are independent, one round trip for all peers) and one system-scope fence makes
+// the poll an acquire; the tiles are then fetched by the async proxy (bulk
+// copies), hence the proxy fence.
 __device__ __forceinline__ bool wait_for_peers_one_thread(const PeerExchange &X, unsigned long long step,
                                                           const WaitPolicy &wp)
 {
+    const long long t0 = clock64();
+    unsigned int polls = 0;
     bool ok = true;
-    for (int r = 0; r < X.nranks && ok; ++r) {
-        if (r != X.rank) ok = spin_until_reached<true>(X.flags + r, step, wp, kStatusPeerTimeout);
+    for (;;) {
+        unsigned long long lowest = ~0ull;
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+            if (r < X.nranks && r != X.rank) lowest = min(lowest, ld_relaxed_sys(X.flags + r));
+        }
+        if (lowest >= step) break;
+        if ((++polls & 63u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned int *>(wp.status) != 0u) { ok = false; break; }
+            if (wp.timeout_cycles > 0 && clock64() - t0 > wp.timeout_cycles) {
+                if (atomicCAS(wp.status, 0u, kStatusPeerTimeout) == 0u && wp.host_status != nullptr) {
+                    *reinterpret_cast<volatile unsigned int *>(wp.host_status) = kStatusPeerTimeout;
+                    __threadfence_system();
+                }
+                ok = false;
+                break;
+            }
+        }
+        __nanosleep(40);
     }
+    __threadfence_system();
     asm volatile("fence.proxy.async.global;" ::: "memory");
     return ok;
 }
@@ -490,9 +526,10 @@ __device__ __forceinline__ void consume_tile(const double2 *__restrict__ sp, con
                                              double (&ax)[R], double (&ay)[R],
                                              const int64_t (&gi)[R], int64_t gj0)
 {
-    // pairs per unrolled iteration, measured (profiles/r2_unroll_ab.log): 16 whatever R is, except the
-    // general-mass loop of the 4-bodies-per-thread shape, which schedules best with 32
-    constexpr int kUnroll = ((!FOLD && R == 4) ? kPairsPerIterationGeneralR4 : kPairsPerIteration) / R;
+    // pairs per unrolled iteration, measured (profiles/r2_unroll_ab.log): 16 for R = 1 and 2, 32 for the
+    // 4-bodies-per-thread shape (same instruction counts either way; ptxas' register assignment
+    // decides +-1 %)
+    constexpr int kUnroll = (R == 4 ? (FOLD ? kPairsPerIterationFoldR4 : kPairsPerIterationGeneralR4) : kPairsPerIteration) / R;
 #pragma unroll kUnroll
     for (int j = 0; j < kTile; ++j) {
         const double2 pj = sp[j];
@@ -615,27 +652,43 @@ __device__ __noinline__ void commit_slice(const TiledParams &P, const double2 *p
         if (owner) commit_body(P, pos_cur, nxt, li0 + bi, sx, sy, ring_row);
     }
 
-    // ---- this slice is done; the last one hands the block (and the step) on ----
+    // ---- this slice is done; the last one marks the block ready for the next step ----
+    // Only what the NEXT STEP ON THIS DEVICE needs happens here: a gpu-scope fence and the
+    // block's counters.  Making the stores to the peers visible costs a system-scope fence
+    // (an NVLink round trip); that is done once per CTA and step, off this path (peer_handover).
     __syncthreads();
     if (tid == 0) {
-        if (P.px.enabled && !P.export_accel) __threadfence_system();    // this CTA's stores to the peers
-        else __threadfence();
+        __threadfence();
         const unsigned long long slices = atomicAdd(P.slices_done + iblock, 1ull) + 1ull;
-        int last_block = 0;
-        if (slices == (unsigned long long)rows * (epoch + 1)) {
+        if (slices == (unsigned long long)rows * (epoch + 1) && !P.export_accel) {
             __threadfence();
-            if (!P.export_accel) st_release_gpu(P.iblock_ready + iblock, step_after);
-            const unsigned long long blocks = atomicAdd(P.iblocks_done, 1ull) + 1ull;
-            if (blocks == (unsigned long long)P.n_iblock * (epoch + 1)) {
-                last_block = 1;
-                if (P.px.enabled && !P.export_accel) __threadfence_system();
-            }
+            st_release_gpu(P.iblock_ready + iblock, step_after);
         }
-        *s_nbad = last_block;
     }
-    __syncthreads();
-    if (*s_nbad && P.px.enabled && !P.export_accel) publish_step(P.px, step_after);
-    __syncthreads();
+}
+
+// After a CTA has committed all its slices of a step: warp 1 makes the CTA's stores to the
+// peers visible system-wide (ONE system-scope fence per CTA and step, while thread 0 already
+// waits for the next step's i-blocks) and counts the CTA's slices; the rank's last CTA of the
+// step publishes the step number to every peer, one lane per peer.  The peers need that only
+// when they reach this rank's tiles, which every CTA schedules after its own shard's.
+template <int THREADS>
+__device__ __noinline__ void peer_handover(const TiledParams &P, int n_slices, unsigned long long step_after)
+{
+    const int tid = threadIdx.x;
+    if ((tid >> 5) != 1) return;
+    const int lane = tid & 31;
+    unsigned long long sent = 0;
+    if (lane == 0) {
+        __threadfence_system();
+        sent = atomicAdd(P.xfer_done, (unsigned long long)n_slices) + (unsigned long long)n_slices;
+    }
+    sent = __shfl_sync(0xffffffffu, sent, 0);
+    if (sent == P.xfer_base + (unsigned long long)P.n_seg_total * (step_after - P.step_base)) {
+        if (lane == 0) __threadfence_system();       // every other CTA's count was preceded by its fence
+        __syncwarp();
+        if (lane < P.px.nranks && lane != P.px.rank) st_release_sys(P.px.peer_flags[lane] + P.px.rank, step_after);
+    }
 }
 
 #ifndef GRAVITY_TILE_TWOSUM
@@ -850,6 +903,11 @@ __global__ void GRAVITY_KERNEL_BOUNDS(THREADS, MINB) k_tiled_steps(const TiledPa
             commit_slice<THREADS, R>(P, pos_cur, cur ^ 1, sg.iblock, sg.slot, epoch, state_step + 1, ring_row, s_red,
                                      s_bad, &s_nbad, &s_abort);
             if (s_abort) break;
+        }
+        if (P.px.enabled && !P.export_accel && !s_abort) {
+            // the slices' stores were ordered before this point by the CTA barrier at the end of commit_slice
+            __syncthreads();
+            peer_handover<THREADS>(P, seg_end - seg_begin, state_step + 1);
         }
         if (trace && tid == 0 && step == 0) trace[3] = global_timer_ns();
     }
@@ -1284,6 +1342,41 @@ __global__ void k_unpack_pairs(const double2 *__restrict__ src, double *a, doubl
         const double2 v = src[i];
         a[i] = v.x;
         b[i] = v.y;
+    }
+}
+
+// The same for page-locked host arrays, which the device reads and writes in place over
+// PCIe (no staging copies, one launch): the path of callers that keep their SoA state in
+// pinned memory, where the fixed costs of five small copies would otherwise dominate a
+// step of a few hundred microseconds.
+__global__ void k_upload_shard_pinned(const double *__restrict__ x, const double *__restrict__ y,
+                                      const double *__restrict__ vx, const double *__restrict__ vy,
+                                      const double *__restrict__ mass, double2 *pos, double2 *vel, double *mass_dev,
+                                      int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        pos[i] = make_double2(x[i], y[i]);
+        vel[i] = make_double2(vx[i], vy[i]);
+        if (mass != nullptr) mass_dev[i] = mass[i];
+    }
+}
+
+__global__ void k_download_shard_pinned(const double2 *__restrict__ pos, const double2 *__restrict__ vel,
+                                        double *x, double *y, double *vx, double *vy, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        if (x != nullptr || y != nullptr) {
+            const double2 p = pos[i];
+            if (x != nullptr) x[i] = p.x;
+            if (y != nullptr) y[i] = p.y;
+        }
+        if (vx != nullptr || vy != nullptr) {
+            const double2 v = vel[i];
+            if (vx != nullptr) vx[i] = v.x;
+            if (vy != nullptr) vy[i] = v.y;
+        }
     }
 }
 

@@ -27,11 +27,11 @@ def check_line(d, reference=False):
 
 
 def test_recorded_gpu_line_meets_the_contract():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_1gpu_final.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_1gpu.json")))
     check_line(d)
     n = d["config"]["bodies"]
     assert abs(d["value"] - n * (n - 1) / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-9
-    assert d["gpu_launches"] == d["steps"]                       # one kernel per step
+    assert d["gpu_launches"] == 1 and d["variant"]["steps_per_launch"] == d["steps"]     # the whole batch in one launch
     assert d["e2e"]["h2d_bytes_per_step"] == 5 * 8 * n and d["e2e"]["d2h_bytes_per_step"] == 4 * 8 * n
     assert 0 < d["e2e"]["value"] <= d["value"] * 1.01
     r = d["roofline"]
@@ -42,14 +42,36 @@ def test_recorded_gpu_line_meets_the_contract():
     assert c["sm_mhz"] <= c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown",
                                                                        "sw_thermal_slowdown"}
     assert d["cpu_baseline"]["value"] < d["value"] / 50
+    check_parity(d["parity"], 1)
+    # both arms name the workload identically (the driver compares them)
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_reference_arm.json")))
+    check_line(ref, reference=True)
+    assert ref["config"] == d["config"]
+    assert ref["full_step_ms_extrapolated"] > 100 * ref["ms_per_step"]       # ms_per_step is what was really timed
+
+
+def check_parity(p, world):
+    """The in-run parity record every line carries."""
+    assert p["rows"] >= 512 and p["ranks_compared"] == world and p["ranks_bit_identical"] is True
+    assert p["max_rel_vs_ref_with_floor"] <= 1e-12 and p["n_above_1e-12"] <= 1 and p["pass"] is True
+    assert p["floor_used"] == (p["n_above_1e-12"] > 0) and "1e-12" in p["gate"]
+    assert p["max_rel_vs_long_double"] <= p["ref_max_rel_vs_long_double"]   # no farther from truth than the reference
 
 
 def test_recorded_multi_gpu_lines():
-    for name, gpus in (("r1_scale_g4_n1048576.json", 4), ("r1_scale_g8_n1048576.json", 8)):
-        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_scale_g*_n*_x*.json")))
+    assert len(paths) >= 6
+    for path in paths:
+        d = json.load(open(path))
         check_line(d)
-        assert d["n_gpus"] == gpus and d["scaling"] == "strong" and "cpu_baseline" not in d
-        assert d["e2e"]["h2d_bytes_per_step"] == 5 * 8 * d["config"]["bodies"] * gpus
+        gpus, n = d["n_gpus"], d["config"]["bodies"]
+        assert "_g%d_n%d_x%d" % (gpus, n, d["variant"]["exchange"] if gpus > 1 else 1) in path
+        assert d["scaling"] == "strong" and "cpu_baseline" not in d
+        # every rank copies only its own shard: totals do not grow with the number of GPUs
+        assert d["e2e"]["h2d_bytes_per_step"] == 5 * 8 * n and d["e2e"]["d2h_bytes_per_step"] == 4 * 8 * n
+        check_parity(d["parity"], gpus)
+        assert d["roofline"]["job_frac_of_nominal"] >= 0.60, path          # north_star's bar, every cell
 
 
 def test_reference_arm_live():
