@@ -616,9 +616,20 @@ int enqueue_steps(gravity_cuda_t *h, double dt, long long nsteps, bool export_ac
                 StepClock probe = host_clk;
                 const long long ring_row = export_accel ? -1 : clock_tick(probe);
                 const CommitParams P = commit_params(h, c, dt, export_accel, ring_row);
-                const int grid = (int)((c.n_local + kStrictThreads - 1) / kStrictThreads);
+                // few bodies per CTA when the shard is small (every SM gets work), at most kStrictMaxBodies
+                const int per_cta = (int)std::max<int64_t>(1, std::min<int64_t>(kStrictMaxBodies,
+                                                                               (c.n_local + 3 * c.num_sms - 1) / (3 * c.num_sms)));
+                const int grid = (int)((c.n_local + per_cta - 1) / per_cta);
+                const size_t smem = strict_smem_bytes(per_cta);
+                CUDA_TRY(h, cudaFuncSetAttribute(k_strict_terms, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)strict_smem_bytes(kStrictMaxBodies)));
                 hot_event(h, c);
-                k_strict_rows<<<grid, kStrictThreads, 0, c.stream>>>(P);
+                if (c.n_local > kStrictRowsFrom) {
+                    k_strict_rows<<<(unsigned)((c.n_local + kStrictRowThreads - 1) / kStrictRowThreads), kStrictRowThreads, 0,
+                                    c.stream>>>(P);
+                } else {
+                    k_strict_terms<<<grid, kStrictThreads, smem, c.stream>>>(P, per_cta);
+                }
                 hot_event(h, c);
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());

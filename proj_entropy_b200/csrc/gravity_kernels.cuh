@@ -924,13 +924,149 @@ __global__ void k_publish_only(const PeerExchange X, unsigned long long step)
 // STRICT kernels: bit-identical to the reference loop
 // ---------------------------------------------------------------------------
 
-// Any N: one thread per local i-body, j ascending through shared-memory tiles.
-constexpr int kStrictThreads = 128;
+// Any N, any number of GPUs, one launch per step.  A CTA owns up to kStrictMaxBodies
+// consecutive i-bodies.  The N pair terms tmp*XDIST, tmp*YDIST of a body (sim_gravity.c:
+// 1202-1204) do not depend on one another, so warps 1..7 evaluate them side by side -- one
+// j-body per thread and chunk, IEEE sqrt and divide, the latency chains that make a serial
+// j loop slow running in parallel -- into a shared-memory buffer, while warp 0 adds the
+// PREVIOUS chunk's terms to each body's sum in ascending j, one lane per body, exactly as
+// the reference adds them.  A skipped pair (:1191, :1199-1201) is stored as +0.0: adding it
+// leaves every sum a reference run can reach unchanged (a sum that starts at +0.0 never
+// becomes -0.0).  Bit-identical to the reference; throughput set by the term arithmetic,
+// not by the number of bodies a shard happens to have.
+constexpr int kStrictThreads   = 256;
+constexpr int kStrictChunk     = kStrictThreads - 32;   // j-bodies per chunk: one per evaluating thread
+constexpr int kStrictRow       = kStrictChunk + 1;      // padded row of the term buffer (bank spread)
+constexpr int kStrictMaxBodies = 8;                     // i-bodies per CTA
 
-__global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitParams P)
+__host__ __device__ inline size_t strict_smem_bytes(int bodies_per_cta)
 {
-    __shared__ double2 s_pos[kStrictThreads];
-    __shared__ double  s_mass[kStrictThreads];
+    return (size_t)2 * bodies_per_cta * kStrictRow * sizeof(double2);
+}
+
+__global__ void __launch_bounds__(kStrictThreads) k_strict_terms(const CommitParams P, int bodies_per_cta)
+{
+    extern __shared__ __align__(16) unsigned char strict_smem[];
+    __shared__ double2 s_drift[kStrictMaxBodies];
+    __shared__ int     s_flag;
+    double2 *s_term = reinterpret_cast<double2 *>(strict_smem);      // [2][bodies_per_cta][kStrictRow]
+
+    const int     tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int     B   = bodies_per_cta;
+    const int64_t l0  = (int64_t)blockIdx.x * B;                      // first local body of this CTA
+    const int     nb  = (int)min((int64_t)B, P.n_local - l0);
+    const bool    owner = warp == 0 && lane < nb;                     // lane b owns body l0 + b
+    const int64_t gi0 = P.i_global0 + l0;
+
+    if (P.px.enabled) {
+        // the peers' positions of this step must have landed before pos_cur is read
+        if (tid == 0) s_flag = wait_for_peers_one_thread(P.px, P.wait_step, P.wp) ? 1 : 0;
+        __syncthreads();
+        if (!s_flag) return;                     // timed out: store nothing, publish nothing
+    }
+    double2 p = make_double2(0.0, 0.0), v = make_double2(0.0, 0.0);
+    if (owner) {
+        p = P.pos_cur[gi0 + lane];
+        v = P.vel[l0 + lane];
+        s_drift[lane] = make_double2(half_drift(p.x, v.x, P.dt), half_drift(p.y, v.y, P.dt));
+    }
+    __syncthreads();
+
+    const int64_t nchunks = (P.n + kStrictChunk - 1) / kStrictChunk;
+    double sx = 0.0, sy = 0.0;
+    // the evaluating threads keep the next chunk's j-body in flight while they work on this one
+    const int t = tid - 32;
+    double2 pj = make_double2(0.0, 0.0);
+    double  mj = 0.0;
+    if (warp >= 1 && t < P.n) {
+        pj = P.pos_cur[t];
+        mj = P.mass[t];
+    }
+    for (int64_t c = 0; c <= nchunks; ++c) {
+        if (warp >= 1) {
+            if (c < nchunks) {
+                const int64_t j = c * kStrictChunk + t;
+                const double2 cur_p = pj;
+                const double  cur_m = mj;
+                const int64_t jn = j + kStrictChunk;
+                if (jn < P.n) {
+                    pj = P.pos_cur[jn];
+                    mj = P.mass[jn];
+                }
+                if (j < P.n) {
+                    double2 *dst = s_term + (size_t)(c & 1) * B * kStrictRow + t;
+                    for (int b = 0; b < nb; ++b) {
+                        const double2 d  = s_drift[b];
+                        const double  dx = __dsub_rn(cur_p.x, d.x);
+                        const double  dy = __dsub_rn(cur_p.y, d.y);
+                        const double  r  = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                        double2 term = make_double2(0.0, 0.0);
+                        if (j != gi0 + b && r != 0.0) {                  // sim_gravity.c:1191, :1199-1201
+                            const double w = __ddiv_rn(cur_m, __dmul_rn(__dmul_rn(r, r), r));   // :1202
+                            term = make_double2(__dmul_rn(w, dx), __dmul_rn(w, dy));
+                        }
+                        dst[(size_t)b * kStrictRow] = term;
+                    }
+                }
+            }
+        } else if (owner && c >= 1) {
+            const int64_t j0  = (c - 1) * kStrictChunk;
+            const int     cnt = (int)min((int64_t)kStrictChunk, P.n - j0);
+            const double2 *row = s_term + ((size_t)((c - 1) & 1) * B + lane) * kStrictRow;
+#pragma unroll 4
+            for (int jj = 0; jj < cnt; ++jj) {
+                sx = __dadd_rn(sx, row[jj].x);                           // :1203
+                sy = __dadd_rn(sy, row[jj].y);                           // :1204
+            }
+        }
+        __syncthreads();
+    }
+    if (owner) {
+        const int64_t li = l0 + lane, gi = gi0 + lane;
+        double nx, ny, nvx, nvy, ax, ay;
+        kick_drift(sx, P.dt, p.x, v.x, nx, nvx, ax);
+        kick_drift(sy, P.dt, p.y, v.y, ny, nvy, ay);
+        if (P.export_accel) {
+            P.accel_out[li] = make_double2(ax, ay);          // sim_gravity.c:1207-1208
+        } else {
+            const double2 pn = make_double2(nx, ny);
+            P.pos_next[gi] = pn;                             // NEXT_X, NEXT_Y  (:1218-1219)
+            P.vel[li]      = make_double2(nvx, nvy);         // NEXT_VX, NEXT_VY (:1220-1221)
+            if (P.px.enabled) {
+                for (int r = 0; r < P.px.nranks; ++r) {
+                    if (r != P.px.rank) P.px.peer_pos[P.cur_next][r][gi] = pn;
+                }
+            }
+            if (P.ring_row) P.ring_row[gi] = pn;             // PATH sample on a day change (:1248-1251)
+        }
+    }
+    if (P.px.enabled && !P.export_accel) {
+        // when the last CTA gets here all new positions of this rank are visible
+        // system-wide and the step number goes to every peer
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(P.commit_counter, 1u);
+            s_flag = (prev == gridDim.x - 1) ? 1 : 0;
+            if (s_flag) *P.commit_counter = 0u;              // ready for the next launch
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (s_flag) publish_step(P.px, P.publish_step);
+    }
+}
+
+// Large shards (more than kStrictRowsFrom bodies on a device): one thread per local i-body, j
+// ascending through shared-memory tiles.  With that many bodies every SM is full of
+// independent sqrt/divide chains and the serial j loop costs nothing; below, the
+// term-parallel kernel above is 1.5-11x faster (measured crossover ~65K bodies).
+constexpr int64_t kStrictRowsFrom = 65536;
+constexpr int kStrictRowThreads = 128;
+
+__global__ void __launch_bounds__(kStrictRowThreads) k_strict_rows(const CommitParams P)
+{
+    __shared__ double2 s_pos[kStrictRowThreads];
+    __shared__ double  s_mass[kStrictRowThreads];
     __shared__ int     s_flag;
 
     const int64_t li     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -950,7 +1086,7 @@ __global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitPara
         px = half_drift(p.x, v.x, P.dt);
         py = half_drift(p.y, v.y, P.dt);
     }
-    for (int64_t j0 = 0; j0 < P.n; j0 += kStrictThreads) {
+    for (int64_t j0 = 0; j0 < P.n; j0 += kStrictRowThreads) {
         const int64_t j = j0 + threadIdx.x;
         __syncthreads();
         if (j < P.n) {
@@ -958,7 +1094,7 @@ __global__ void __launch_bounds__(kStrictThreads) k_strict_rows(const CommitPara
             s_mass[threadIdx.x] = P.mass[j];
         }
         __syncthreads();
-        const int cnt = (int)min((int64_t)kStrictThreads, P.n - j0);
+        const int cnt = (int)min((int64_t)kStrictRowThreads, P.n - j0);
         if (active) {
             for (int jj = 0; jj < cnt; ++jj) {
                 if (j0 + jj == gi) continue;             // sim_gravity.c:1191

@@ -72,6 +72,25 @@ def test_strict_kernels_bits_vs_oracle(n):
         assert bits_equal(a, b)
 
 
+def test_strict_large_shard_takes_the_row_kernel_and_stays_bit_exact():
+    """Above 65,536 bodies per device STRICT mode switches from the term-parallel kernel to one
+    thread per body; both must give the reference's bits (accelerations and one step)."""
+    n = 66000
+    m, x, y, vx, vy = g.plummer(n, seed=23)
+    x[500], y[500] = x[64000], y[64000]                    # a coincident pair across the two halves
+    vx[64000] = vy[64000] = 0.0
+    with g.GravityCuda(n, kernel=g.KERNEL_STRICT) as h:
+        h.upload(m, x, y, vx, vy)
+        ax, ay = h.accel(3)
+        h.step(3, 1)
+        got = h.download()
+    rax, ray = oracle.accel(m, x, y, vx, vy, 3, nthreads=NTHREADS)
+    assert bits_equal(ax, rax) and bits_equal(ay, ray)
+    want = oracle.step(m, x, y, vx, vy, 3, 1, nthreads=NTHREADS)
+    for a, b in zip(got, want):
+        assert bits_equal(a, b)
+
+
 def test_strict_200_bodies_with_coincident_pairs():
     """The reference's MAX_OBJECT-sized case on the cooperative kernel, with exact
     duplicates (r == 0 skip) and a massless body."""
