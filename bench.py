@@ -13,9 +13,9 @@ i-bodies sharded over the ranks, positions all-gathered with NCCL every step.
 One JSON line on stdout (rank 0):
   value     whole-job pairs/s with the state resident in HBM, K steps timed with
             CUDA events on the library's compute stream, max over ranks
-  e2e       the same through the C ABI with HOST buffers: upload + step +
-            download per step, wall clock; every rank moves only its own shard
-            over PCIe (40*N bytes in, 32*N bytes out per step in total)
+  e2e       the same through the C ABI with HOST buffers: one gravity_cuda_step_host
+            call per step (upload + step + download), wall clock; every rank moves
+            only its own shard over PCIe (40*N bytes in, 32*N bytes out per step in total)
   parity    after the timed steps, outside the timed region: accelerations of the
             state the run ended in, on a row sample, against the oracle (CPU
             restatement of the reference loop) and against a long-double sum, and
@@ -93,7 +93,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--bodies", type=int, default=1 << 20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(--steps, 5)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(--steps, 5), or 50 up to 262,144 bodies")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0)
@@ -400,26 +400,20 @@ def run_ours(args, rank, world, local_rank, ranks=None):
     # every step: host -> device of that step's inputs, one step, device -> host of its
     # result.  Each rank moves only its own shard over PCIe (upload reads nothing else,
     # download_scope = 1 writes nothing else); the devices complete each other over NVLink.
-    e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))     # bounded so that large --steps stay in minutes
+    e2e_steps = args.e2e_steps or max(1, min(args.steps, 50 if n <= (1 << 18) else 5))    # bounded: minutes at most
     lo, hi = shard_bounds(n, world, rank)
     pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in state]
-    out = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(4)]
+    ptrs = [t.data_ptr() for t in pinned]
     if world > 1:
         h.set_option("download_scope", 1)
-    h.upload_ptrs(*[t.data_ptr() for t in pinned])          # warm the path once
-    h.step(DT, 1)
-    h.download_ptrs(*[t.data_ptr() for t in out])
+    h.step_host_ptrs(*ptrs, DT, 1)                           # warm the path once
     barrier()
     torch.cuda.synchronize()
     te0 = time.perf_counter()
     for _ in range(e2e_steps):
-        h.upload_ptrs(pinned[0].data_ptr(), pinned[1].data_ptr(), pinned[2].data_ptr(), pinned[3].data_ptr(),
-                      pinned[4].data_ptr())
-        h.step(DT, 1)
-        h.download_ptrs(*[t.data_ptr() for t in out])
-        # next step's input is this step's output: swap the pinned buffers
-        for k in range(4):
-            pinned[k + 1], out[k] = out[k], pinned[k + 1]
+        # one C-ABI call per step: host arrays in, one step, host arrays out (updated in place, so
+        # the next step's input is this step's output)
+        h.step_host_ptrs(*ptrs, DT, 1)
     torch.cuda.synchronize()
     barrier()
     te = max_over_ranks(time.perf_counter() - te0)

@@ -175,6 +175,15 @@ int gravity_cuda_path_read(gravity_cuda_t *h, int64_t first, int64_t count, doub
  * doubles each); the state is not advanced. */
 int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay);
 
+/* The same path for a host that keeps its state as SoA arrays: upload (rules of
+ * gravity_cuda_upload; mass may be NULL after the first upload), nsteps steps and
+ * the download back INTO x, y, vx, vy (rules of gravity_cuda_download, incl.
+ * "download_scope") as one call: everything is enqueued back to back and waited
+ * for once, which is what matters when a step lasts a few hundred microseconds.
+ * Page-locked arrays are read and written in place by the device. */
+int gravity_cuda_step_host(gravity_cuda_t *h, const double *mass, double *x, double *y,
+                           double *vx, double *vy, int32_t dt, int64_t nsteps);
+
 /* AoS convenience for the reference host: gathers MASS,X,Y,VX,VY from n
  * object_t-like records reached through objects[i] by byte offset (X@32, Y@40,
  * VX@48, VY@56, MASS@64 in sim_gravity.c:83-105), steps, and scatters

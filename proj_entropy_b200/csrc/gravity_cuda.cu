@@ -1066,8 +1066,9 @@ static double *pinned_alias(const double *p)
     return a.type == cudaMemoryTypeHost ? static_cast<double *>(a.devicePointer) : nullptr;
 }
 
-int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, const double *y,
-                        const double *vx, const double *vy)
+// Enqueues the whole upload; the host arrays are consumed once every device's ev_copy has fired.
+static int upload_enqueue(gravity_cuda_t *h, const double *mass, const double *x, const double *y,
+                          const double *vx, const double *vy)
 {
     if (!h) return fail(nullptr, "upload: NULL handle");
     if (h->dead) return fail(h, "the handle is dead: a device-side wait timed out earlier");
@@ -1133,12 +1134,19 @@ int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, 
         }
     }
     h->cur = 0;
+    if (mass) h->mass_uploaded = true;
+    h->uploaded = true;
+    return 0;
+}
+
+int gravity_cuda_upload(gravity_cuda_t *h, const double *mass, const double *x, const double *y,
+                        const double *vx, const double *vy)
+{
+    if (upload_enqueue(h, mass, x, y, vx, vy) != 0) return -1;
     for (DeviceCtx &c : h->ctx) {
         CUDA_TRY(h, cudaSetDevice(c.device));
         CUDA_TRY(h, cudaEventSynchronize(c.ev_copy));
     }
-    if (mass) h->mass_uploaded = true;
-    h->uploaded = true;
     return 0;
 }
 
@@ -1183,7 +1191,8 @@ static int download_gathered(gravity_cuda_t *h, const double2 *shard, double *a,
     return 0;
 }
 
-int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, double *vy)
+// Enqueues the whole download; the host arrays are complete after the streams have been synchronised.
+static int download_enqueue(gravity_cuda_t *h, double *x, double *y, double *vx, double *vy)
 {
     if (!h) return fail(nullptr, "download: NULL handle");
     if (!h->uploaded) return fail(h, "download before upload");
@@ -1204,8 +1213,7 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
             }
-            if (sync_all(h) != 0) return -1;
-            return check_status(h);
+            return 0;
         }
     }
     if (x || y) {
@@ -1230,6 +1238,12 @@ int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, d
             if (download_gathered(h, h->ctx[0].vel, vx, vy, 2) != 0) return -1;
         }
     }
+    return 0;
+}
+
+int gravity_cuda_download(gravity_cuda_t *h, double *x, double *y, double *vx, double *vy)
+{
+    if (download_enqueue(h, x, y, vx, vy) != 0) return -1;
     if (sync_all(h) != 0) return -1;
     return check_status(h);
 }
@@ -1413,6 +1427,23 @@ int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay)
     } else {
         if (download_gathered(h, h->ctx[0].accel, ax, ay, 0) != 0) return -1;
     }
+    if (sync_all(h) != 0) return -1;
+    return check_status(h);
+}
+
+static int step_impl(gravity_cuda_t *h, int32_t dt, int64_t nsteps, StepClock *clk);
+
+int gravity_cuda_step_host(gravity_cuda_t *h, const double *mass, double *x, double *y, double *vx, double *vy,
+                           int32_t dt, int64_t nsteps)
+{
+    if (!h) return fail(nullptr, "step_host: NULL handle");
+    // upload, the steps and the download are enqueued back to back and waited for once
+    if (upload_enqueue(h, mass, x, y, vx, vy) != 0) return -1;
+    StepClock off;
+    memset(&off, 0, sizeof(off));
+    off.dt = dt;
+    if (step_impl(h, dt, nsteps, &off) != 0) return -1;
+    if (download_enqueue(h, x, y, vx, vy) != 0) return -1;
     if (sync_all(h) != 0) return -1;
     return check_status(h);
 }

@@ -24,6 +24,27 @@ class GravityError(RuntimeError):
     pass
 
 
+def _preload_bundled_nccl():
+    """libgravity_cuda links libnccl.so.2.  A process can hold only one library of that soname: if
+    the system's NCCL gets in first, a later `import torch` fails, because torch's CUDA library needs
+    symbols of the newer NCCL that ships with it (site-packages/nvidia/nccl).  So when that bundled
+    NCCL exists it is loaded first -- the C ABI of libnccl.so.2 is backward compatible, and it is the
+    one in use anyway whenever torch was imported before this module (bench.py, the rank workers)."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load_cuda_library():
     """Load proj_entropy_b200/libgravity_cuda.so and declare every prototype."""
     global _LIB
@@ -34,6 +55,7 @@ def load_cuda_library():
     if not os.path.exists(path):
         raise GravityError("%s is not built (run `make` or __graft_entry__.build()); "
                            "there is no fallback implementation" % path)
+    _preload_bundled_nccl()
     lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     H = C.c_void_p
     sigs = {
@@ -52,6 +74,7 @@ def load_cuda_library():
         "gravity_cuda_step": (C.c_int, [H, C.c_int32, C.c_int64]),
         "gravity_cuda_step_async": (C.c_int, [H, C.c_int32, C.c_int64]),
         "gravity_cuda_sync": (C.c_int, [H]),
+        "gravity_cuda_step_host": (C.c_int, [H, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_int64]),
         "gravity_cuda_accel": (C.c_int, [H, C.c_int32, _dp, _dp]),
         "gravity_cuda_step_objects": (C.c_int, [H, C.POINTER(C.c_void_p), C.c_int64, C.c_size_t, C.c_size_t,
                                                 C.c_size_t, C.c_size_t, C.c_size_t, C.c_int32, C.c_int64]),
@@ -247,6 +270,21 @@ class GravityCuda:
         self._check(self._lib.gravity_cuda_trace_read(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap,
                                                       C.byref(n)))
         return buf[:min(cap, n.value)]
+
+    def step_host(self, mass, x, y, vx, vy, dt, nsteps=1):
+        """upload + nsteps + download in one call; x, y, vx, vy (contiguous float64 arrays) are
+        updated in place, mass may be None after the first upload."""
+        for a in (x, y, vx, vy):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n,)):
+                raise ValueError("step_host updates contiguous float64 arrays of length n in place")
+        m = None if mass is None else _ptr(_f64(mass, self.n))
+        self._check(self._lib.gravity_cuda_step_host(self._h, m, _ptr(x), _ptr(y), _ptr(vx), _ptr(vy), int(dt), int(nsteps)))
+
+    def step_host_ptrs(self, mass, x, y, vx, vy, dt, nsteps=1):
+        """Raw host addresses (e.g. pinned torch tensors' data_ptr()); mass may be 0/None."""
+        cast = lambda p: C.cast(C.c_void_p(int(p)), _dp) if p else None
+        self._check(self._lib.gravity_cuda_step_host(self._h, cast(mass), cast(x), cast(y), cast(vx), cast(vy),
+                                                     int(dt), int(nsteps)))
 
     def accel(self, dt):
         ax = np.zeros(self.n, dtype=np.float64)

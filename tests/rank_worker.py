@@ -65,6 +65,14 @@ mine = h.download()
 lo, hi = shard_bounds(n, r.world, r.rank)
 res["shard_download_ok"] = bool(all(np.array_equal(a[lo:hi], b[lo:hi]) for a, b in zip(mine, got)) and
                                 all(not a[:lo].any() and not a[hi:].any() for a in mine))
+# the one-call path on the shard: upload + 2 steps + download, in place, compared with stepping on
+hx, hy, hvx, hvy = (a.copy() for a in got)
+h.step_host(m, hx, hy, hvx, hvy, 3, 2)
+h.step(3, 0)
+h.upload(None, *got)
+h.step(3, 2)
+two = h.download()
+res["step_host_ok"] = bool(all(np.array_equal(a[lo:hi], b[lo:hi]) for a, b in zip((hx, hy, hvx, hvy), two)))
 h.set_option("download_scope", 0)
 # a second upload must be safe while peers are connected; the masses stay (mass = None)
 h.upload(None, x, y, vx, vy)

@@ -69,3 +69,16 @@ def test_product_does_not_reference_the_oracle():
                     assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)
     ldd = os.popen("ldd %s" % os.path.join(ROOT, "proj_entropy_b200", "libgravity_cuda.so")).read()
     assert "oracle" not in ldd
+
+
+def test_torch_can_be_imported_after_the_cuda_library():
+    """Both link libnccl.so.2 and a process holds one library per soname: with the system's NCCL in
+    first, torch's CUDA library would miss symbols of the newer NCCL it ships with.  The ctypes
+    mirror therefore loads that bundled NCCL first; either import order must work."""
+    import subprocess
+    import sys
+    for code in ("import proj_entropy_b200 as g; g.load_cuda_library(); import torch; print(torch.__version__)",
+                 "import torch; import proj_entropy_b200 as g; g.load_cuda_library(); print(torch.__version__)"):
+        p = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           timeout=300, cwd=ROOT)
+        assert p.returncode == 0, p.stderr[-1500:]

@@ -341,6 +341,38 @@ def test_upload_without_masses_keeps_them():
         assert bits_equal(p, q) and bits_equal(p, r)
 
 
+def test_step_host_is_upload_step_download_in_one_call():
+    """gravity_cuda_step_host: pageable arrays (staging copies) and page-locked ones (read and
+    written in place by the device), masses optional after the first call, arrays updated in place."""
+    import torch
+    n = 6000
+    m, x, y, vx, vy = g.plummer(n, seed=18)
+    with g.GravityCuda(n, kernel=g.KERNEL_TILED) as h:
+        h.upload(m, x, y, vx, vy)
+        h.step(4, 3)
+        want3 = h.download()
+        h.step(4, 2)
+        want5 = h.download()
+    for pinned in (False, True):
+        arrs = [a.copy() for a in (x, y, vx, vy)]
+        keep = None
+        if pinned:
+            keep = [torch.from_numpy(a).pin_memory() for a in arrs]
+            arrs = [t.numpy() for t in keep]
+        with g.GravityCuda(n, kernel=g.KERNEL_TILED) as h:
+            h.step_host(m, *arrs, 4, 3)
+            for a, b in zip(arrs, want3):
+                assert bits_equal(a, b), pinned
+            h.step_host(None, *arrs, 4, 2)                   # the masses stay on the device
+            for a, b in zip(arrs, want5):
+                assert bits_equal(a, b), pinned
+            with pytest.raises(ValueError):
+                h.step_host(m, arrs[0][::2], *arrs[1:], 4, 1)
+    with g.GravityCuda(n) as h:
+        with pytest.raises(g.GravityError, match="mass"):
+            h.step_host(None, x.copy(), y.copy(), vx.copy(), vy.copy(), 1, 1)
+
+
 def test_batches_and_single_steps_give_the_same_bits():
     """One launch for the whole batch (steps chained by per-i-block ready counters) against one
     launch per step: same plan, same summation order, identical bits; and the batch is repeatable."""

@@ -59,7 +59,7 @@ def test_two_ranks_under_torchrun(gpu_count, exchange, tmp_path):
         pytest.skip("needs 2 GPUs")
     n = 20000
     res = run_ranks(tmp_path, 2, exchange, n)
-    assert all(r["world"] == 2 and r["same_after_reupload"] and r["shard_download_ok"] for r in res)
+    assert all(r["world"] == 2 and r["same_after_reupload"] and r["shard_download_ok"] and r["step_host_ok"] for r in res)
     assert res[0]["accel_err"] <= 1e-12
     assert res[0]["pos_err"] <= 1e-12 and res[0]["vel_err"] <= 1e-11 and res[0]["energy_err"] <= 1e-12
     # every rank downloads the same full state
