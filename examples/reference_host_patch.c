@@ -1,10 +1,12 @@
 /*
- * examples/reference_host_patch.c -- the INTEGRATION.md patch as a compilable
- * unit: a record with the reference's object_t layout (sim_gravity.c:83-105),
- * worker-0's RUN body replaced by gravity_cuda_step_objects(), and the
- * unchanged host bookkeeping (day test, PATH ring, sim_time; :1229-1260).
- * tests/test_integration_snippet.py compiles and links it against
- * libgravity_cuda; with a GPU it also runs two_body-like data through it.
+ * examples/reference_host_patch.c -- the seam of patches/sim_gravity_gpu.patch as
+ * a small compilable unit for readers who do not have the reference at hand: a
+ * record with the reference's object_t layout (sim_gravity.c:83-105), worker-0's
+ * RUN body replaced by gravity_cuda_step_objects(), and the unchanged host
+ * bookkeeping (day test, PATH ring, sim_time; :1229-1260).  The patch itself is
+ * applied to the REAL sim_gravity.c and run on the GPU by tests/test_reference_patch.py
+ * (INTEGRATION.md section 2); tests/test_integration_snippet.py compiles and links
+ * this unit against libgravity_cuda and, with a GPU, runs two_body-like data through it.
  */
 #include "gravity_cuda.h"
 
