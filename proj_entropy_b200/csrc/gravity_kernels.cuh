@@ -355,7 +355,7 @@ __device__ __forceinline__ double half_drift(double x, double v, double dt)
 //   r2^(-3/2) = y0^3 * (1-e)^(-3/2) = y0^3 * (1 + e*(3/2 + 15/8 e) + O(e^3)),
 //   |e| < 2^-19 so the dropped term is < 2^-56.
 // r2 == 0 (an exactly coincident pair, :1199-1201) or a non-finite r2 yields a
-// NaN that poisons the sum; commit_iblock detects it and redoes that body on
+// NaN that poisons the sum; commit_slice detects it and redoes that body on
 // the guarded path, which keeps the test out of this loop.
 __device__ __forceinline__ double pair_weight(double dx, double dy, double mj)
 {

@@ -1,7 +1,7 @@
 // tools/fp64_microbench.cu -- developer microbenchmarks of the sm_100a FP64
 // pipe: how many warp-level FP64 instructions per cycle per SM sub-partition
 // does the hardware sustain for different operand patterns?  Informs the
-// instruction budget of k_tiled_accumulate.
+// instruction budget of the tiled pair loop, k_tiled_steps.
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_microbench tools/fp64_microbench.cu
 #include <cstdio>
 #include <cstdlib>
