@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define MAX_OBJECT 200
 #define MAX_NAME 32
@@ -88,8 +89,16 @@ int main(int argc, char **argv)
         fprintf(stderr, "GPU Init Failed: %s\n", gravity_cuda_last_error(NULL));
         return 1;
     }
-    for (i = 0; i < steps; i++) {
-        if (run_one_step() != 0) return 1;
+    {
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (i = 0; i < steps; i++) {
+            if (run_one_step() != 0) return 1;
+        }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        /* what one drop-in call costs: gather, upload, step, download, scatter */
+        fprintf(stderr, "%d steps, %.1f us per gravity_cuda_step_objects call\n", steps,
+                ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 1e3 / (steps > 0 ? steps : 1));
     }
     for (i = 0; i < 2; i++) {
         printf("%s %a %a %a %a\n", sim.object[i]->NAME, sim.object[i]->X, sim.object[i]->Y, sim.object[i]->VX,

@@ -104,6 +104,7 @@ struct gravity_cuda {
     int64_t path_tail = 0;           // samples taken since path_enable
     int64_t launches = 0;
     bool timing = false;
+    double *aos_stage = nullptr;     // page-locked 5*n doubles: SoA image of the caller's records (step_objects)
     char err[200] = "";
 };
 
@@ -910,6 +911,7 @@ void gravity_cuda_destroy(gravity_cuda_t *h)
         if (c.ev_stop) cudaEventDestroy(c.ev_stop);
         if (c.ev_copy) cudaEventDestroy(c.ev_copy);
         if (c.host_status) cudaFreeHost(c.host_status);
+        if (&c == &h->ctx[0] && h->aos_stage) cudaFreeHost(h->aos_stage);
         if (c.stream) cudaStreamDestroy(c.stream);
     }
     delete h;
@@ -1456,8 +1458,13 @@ int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size
     if (n != h->n) return fail(h, "step_objects: n=%lld but the handle was created for %lld", (long long)n,
                                (long long)h->n);
     return no_throw(h, [&]() -> int {
-    std::vector<double> soa((size_t)5 * n);
-    double *m = soa.data(), *x = m + n, *y = x + n, *vx = y + n, *vy = vx + n;
+    // the records are gathered into a page-locked SoA image that the device reads and writes
+    // in place: one upload kernel, the steps, one download kernel, one wait per call
+    if (!h->aos_stage) {
+        CUDA_TRY(h, cudaSetDevice(h->ctx[0].device));
+        CUDA_TRY(h, cudaHostAlloc(&h->aos_stage, sizeof(double) * 5 * (size_t)n, cudaHostAllocPortable));
+    }
+    double *m = h->aos_stage, *x = m + n, *y = x + n, *vx = y + n, *vy = vx + n;
     for (int64_t i = 0; i < n; ++i) {
         const char *o = static_cast<const char *>(objects[i]);
         if (!o) return fail(h, "step_objects: objects[%lld] is NULL", (long long)i);
@@ -1467,9 +1474,11 @@ int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size
         memcpy(&vx[i], o + off_vx, sizeof(double));
         memcpy(&vy[i], o + off_vy, sizeof(double));
     }
-    if (gravity_cuda_upload(h, m, x, y, vx, vy) != 0) return -1;
-    if (gravity_cuda_step(h, dt, nsteps) != 0) return -1;
-    if (gravity_cuda_download(h, x, y, vx, vy) != 0) return -1;
+    const int scope = h->opt_download_scope;
+    h->opt_download_scope = 0;                       // every record is written back, whatever the caller's scope
+    const int rc = gravity_cuda_step_host(h, m, x, y, vx, vy, dt, nsteps);
+    h->opt_download_scope = scope;
+    if (rc != 0) return -1;
     for (int64_t i = 0; i < n; ++i) {
         char *o = static_cast<char *>(objects[i]);
         memcpy(o + off_x, &x[i], sizeof(double));
