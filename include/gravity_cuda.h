@@ -171,6 +171,13 @@ int gravity_cuda_step_path(gravity_cuda_t *h, int32_t dt, int64_t nsteps, int64_
                            int32_t *last_day, int64_t *path_tail);
 int gravity_cuda_path_read(gravity_cuda_t *h, int64_t first, int64_t count, double *x, double *y);
 
+/* Host-only arithmetic (no GPU touched): how many PATH samples nsteps steps of size dt take
+ * from sim_time with the given last_day -- the commit block's day test (sim_gravity.c:
+ * 1232-1236) exactly as the kernels run it; *last_day is advanced.  -1 on a bad argument
+ * (dt < 1, sim_time < 0, nsteps < 0).  In rank mode path_read is collective unless
+ * "download_scope" = 1. */
+int64_t gravity_cuda_path_samples_in(int32_t dt, int64_t nsteps, int64_t sim_time, int32_t *last_day);
+
 /* AX, AY exactly as at sim_gravity.c:1207-1208 for the current state (n
  * doubles each); the state is not advanced. */
 int gravity_cuda_accel(gravity_cuda_t *h, int32_t dt, double *ax, double *ay);

@@ -13,11 +13,11 @@ tests and by bench.py.  It never computes anything itself and has no CPU
 fallback: without the built CUDA library every call raises.
 """
 from .gravity import (GravityCuda, GravityError, KERNEL_AUTO, KERNEL_TILED, KERNEL_STRICT,
-                      device_count, fp64_peak, nccl_unique_id, load_cuda_library, plan_probe)
+                      device_count, fp64_peak, nccl_unique_id, load_cuda_library, plan_probe, path_samples_in)
 from .host import (Scenario, ScenarioError, load_scenario, plummer, steps_until_day_change, load_host_library,
                    snapshot_read, snapshot_write)
 
 __all__ = ["GravityCuda", "GravityError", "KERNEL_AUTO", "KERNEL_TILED", "KERNEL_STRICT",
-           "device_count", "fp64_peak", "nccl_unique_id", "load_cuda_library", "plan_probe",
+           "device_count", "fp64_peak", "nccl_unique_id", "load_cuda_library", "plan_probe", "path_samples_in",
            "Scenario", "ScenarioError", "load_scenario", "plummer", "steps_until_day_change",
            "load_host_library", "snapshot_read", "snapshot_write"]

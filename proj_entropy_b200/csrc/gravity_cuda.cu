@@ -1366,6 +1366,22 @@ int gravity_cuda_step_path(gravity_cuda_t *h, int32_t dt, int64_t nsteps, int64_
     return 0;
 }
 
+int64_t gravity_cuda_path_samples_in(int32_t dt, int64_t nsteps, int64_t sim_time, int32_t *last_day)
+{
+    // host-only: the same clock_tick the kernels run, so that a host can size its buffers
+    if (dt < 1 || sim_time < 0 || nsteps < 0 || !last_day) return -1;
+    StepClock k;
+    memset(&k, 0, sizeof(k));
+    k.dt = dt;
+    k.day = sim_time / 86400;
+    k.rem = sim_time % 86400;
+    k.capacity = 1;
+    k.last_day = *last_day;
+    for (int64_t s = 0; s < nsteps; ++s) clock_tick(k);
+    *last_day = k.last_day;
+    return k.tail;
+}
+
 int gravity_cuda_path_read(gravity_cuda_t *h, int64_t first, int64_t count, double *x, double *y)
 {
     if (!h) return fail(nullptr, "path_read: NULL handle");

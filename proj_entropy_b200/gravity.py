@@ -82,6 +82,7 @@ def load_cuda_library():
         "gravity_cuda_step_path": (C.c_int, [H, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int32),
                                              C.POINTER(C.c_int64)]),
         "gravity_cuda_path_read": (C.c_int, [H, C.c_int64, C.c_int64, _dp, _dp]),
+        "gravity_cuda_path_samples_in": (C.c_int64, [C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int32)]),
         "gravity_cuda_trace_read": (C.c_int, [H, C.POINTER(C.c_uint64), C.c_int64, C.POINTER(C.c_int64)]),
         "gravity_cuda_energy": (C.c_int, [H, _dp, _dp]),
         "gravity_cuda_timer_start": (C.c_int, [H]),
@@ -132,6 +133,17 @@ def fp64_peak(device=0):
     if lib.gravity_cuda_fp64_peak(device, C.byref(tf), C.byref(mhz)) != 0:
         raise GravityError(lib.gravity_cuda_last_error(None).decode())
     return tf.value, mhz.value
+
+
+def path_samples_in(dt, nsteps, sim_time=0, last_day=0):
+    """(PATH samples that nsteps steps of size dt take from sim_time, last_day afterwards): the
+    commit block's day test as the kernels run it, computed on the host (no GPU needed)."""
+    lib = load_cuda_library()
+    ld = C.c_int32(int(last_day))
+    cnt = lib.gravity_cuda_path_samples_in(int(dt), int(nsteps), int(sim_time), C.byref(ld))
+    if cnt < 0:
+        raise GravityError("path_samples_in: dt >= 1, sim_time >= 0 and nsteps >= 0 are required")
+    return cnt, ld.value
 
 
 def plan_probe(n, nranks=1, rank=0, num_sms=148, threads=0, bodies_per_thread=0, ctas_per_sm=0):
