@@ -49,7 +49,7 @@ FP64_NOMINAL_TFLOPS = 37.2     # 148 SM x 64 lanes x 2 x 1.965 GHz (BASELINE.md 
 # masses, velocities read once: 40*N; new positions and velocities written: 32*N) plus the partial-sum rows
 # (written and read once each, hi + lo: 64 bytes per body and segment, ~1,170 segments of 1,024 bodies at this size).
 # Other configurations: not captured.
-NCU_DRAM_BYTES_PER_STEP = {(1 << 20, 1): 71849216 + 57456128}
+NCU_DRAM_BYTES_PER_STEP = {(1 << 20, 1): 72227328 + 58004736}
 DT = 1
 SEED = 1
 

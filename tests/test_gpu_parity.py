@@ -393,6 +393,26 @@ def test_batches_and_single_steps_give_the_same_bits():
         assert np.allclose(a, b, rtol=1e-11, atol=0)
 
 
+@pytest.mark.parametrize("n,threads,bpt,cps", [(1025, 0, 0, 0), (2049, 128, 1, 4), (4097, 128, 2, 3), (4097, 256, 1, 2),
+                                               (9001, 256, 2, 2), (9001, 256, 4, 1), (20011, 0, 0, 0)])
+def test_many_steps_in_one_launch_stay_bit_identical_to_one_launch_per_step(n, threads, bpt, cps):
+    """Stress of the in-kernel data flow (arrival / ready counters, TMA fetches of positions other
+    CTAs have just committed, slices, the two ping-pong buffers): 400 steps in ONE launch against
+    400 launches, small systems where a step is tens of microseconds and CTAs run far apart.
+    Any ordering hole shows up as a differing bit."""
+    m, x, y, vx, vy = g.plummer(n, seed=40 + bpt)
+    opts = dict(threads=threads, bodies_per_thread=bpt, ctas_per_sm=cps) if threads else {}
+    out = []
+    for persistent in (1, 0):
+        with g.GravityCuda(n, kernel=g.KERNEL_TILED, persistent=persistent, **opts) as h:
+            h.upload(m, x, y, vx, vy)
+            h.step(3600, 400)
+            out.append(h.download())
+    for a, b in zip(*out):
+        assert bits_equal(a, b)
+    assert np.isfinite(out[0][0]).all()
+
+
 def test_energy_matches_oracle():
     n = 10000
     m, x, y, vx, vy = g.plummer(n, seed=4)
@@ -493,6 +513,25 @@ def test_two_gpus_agree_with_one(gpu_count, exchange):
     want = oracle.step(m, x, y, vx, vy, 5, 4, nthreads=NTHREADS)
     for a, b in zip(two, want):
         assert np.allclose(a, b, rtol=1e-11, atol=0)
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("n", [3000, 20000])
+def test_two_gpus_both_exchanges_give_the_same_bits_over_many_steps(gpu_count, n):
+    """300 steps in one launch per GPU, chained by peer flags over NVLink, against 300 launches with an
+    NCCL all-gather after each: same plan, same summation order, so every bit must agree -- a stale or
+    torn remote position would not."""
+    if gpu_count < 2:
+        pytest.skip("needs 2 GPUs")
+    m, x, y, vx, vy = g.plummer(n, seed=51)
+    out = []
+    for exchange in (1, 0):
+        with g.GravityCuda(n, ngpus=2, kernel=g.KERNEL_TILED, exchange=exchange) as h:
+            h.upload(m, x, y, vx, vy)
+            h.step(3600, 300)
+            out.append(h.download())
+    for a, b in zip(*out):
+        assert bits_equal(a, b)
 
 
 @pytest.mark.multigpu
