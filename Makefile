@@ -26,7 +26,7 @@ $(PKG)/gravity_headless: $(PKG)/host/gravity_headless.c $(PKG)/libgravity_host.s
 	    -Wl,-rpath,'$$ORIGIN' -lm
 
 # after the CUDA library: oracle/_ref/ref_gravity_gpu (the patched reference unit) links against it
-oracle: $(PKG)/libgravity_cuda.so
+oracle: $(PKG)/libgravity_cuda.so $(PKG)/libgravity_host.so
 	$(MAKE) -C oracle
 
 tools: tools/fp64_microbench tools/fp64_mix

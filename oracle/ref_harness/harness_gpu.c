@@ -30,9 +30,18 @@ extern int gravity_cuda_step_objects(gravity_cuda_t *h, void **objects, int64_t 
                                      size_t off_vx, size_t off_vy, size_t off_mass, int32_t dt, int64_t nsteps);
 extern int usleep(useconds_t usec);
 
-static volatile long long steps_done, steps_target;
+static volatile long long steps_done, steps_target, shim_calls;
 static volatile long long idle_calls;
 static volatile int       step_failed;
+
+/* GPU_BATCHED: the unit was patched with patches/sim_gravity_gpu_batched.patch, whose worker
+ * asks for a whole batch of steps per shim call (up to the next PATH sample, at most
+ * gpu_batch_limit); the harness meters by setting that limit to the steps still wanted. */
+#ifdef GPU_BATCHED
+#define SET_BATCH_LIMIT(n) (gpu_batch_limit = (n) > 0 ? (n) : 1)
+#else
+#define SET_BATCH_LIMIT(n) ((void)0)
+#endif
 
 int hook_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size_t off_x, size_t off_y, size_t off_vx,
                       size_t off_vy, size_t off_mass, int32_t dt, int64_t nsteps)
@@ -42,7 +51,10 @@ int hook_step_objects(gravity_cuda_t *h, void **objects, int64_t n, size_t off_x
         step_failed = 1;
         return rc;
     }
-    if (++steps_done >= steps_target) state = STATE_STOP;   /* the commit block of this step still runs */
+    shim_calls++;
+    steps_done += nsteps;
+    if (steps_done >= steps_target) state = STATE_STOP;     /* the commit block of this step still runs */
+    SET_BATCH_LIMIT(steps_target - steps_done);
     return rc;
 }
 
@@ -59,9 +71,9 @@ static void dump(FILE *out, const char *path, long long steps)
 {
     int i;
     fprintf(out, "{\"scenario\": \"%s\", \"steps\": %lld, \"sim_time\": %lld, \"dt\": %d, \"n\": %d, \"sim_width\": \"%a\", "
-                 "\"path_tail\": %lld, \"path_hash\": \"%016llx\", \"max_thread\": %d, \"bodies\": [",
+                 "\"path_tail\": %lld, \"path_hash\": \"%016llx\", \"max_thread\": %d, \"shim_calls\": %lld, \"bodies\": [",
             path, steps, (long long)sim.sim_time, DT, sim.max_object, sim_width, (long long)path_tail,
-            (unsigned long long)reference_path_digest(), max_thread);
+            (unsigned long long)reference_path_digest(), max_thread, (long long)shim_calls);
     for (i = 0; i < sim.max_object; i++) {
         object_t *o = sim.object[i];
         fprintf(out, "%s{\"name\": \"%s\", \"mass\": \"%a\", \"radius\": \"%a\", \"x\": \"%a\", \"y\": \"%a\", \"vx\": \"%a\", \"vy\": \"%a\"}",
@@ -92,6 +104,7 @@ int main(int argc, char **argv)
         }
         if (target > steps_done && sim.max_object > 0) {
             steps_target = target;
+            SET_BATCH_LIMIT(target - steps_done);
             __sync_synchronize();
             state = STATE_RUN;                 /* what the RUN button does, sim_gravity.c:953-955 */
             while (steps_done < target && !step_failed) usleep(50);

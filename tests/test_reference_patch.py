@@ -21,8 +21,11 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import apply_reference_patch as arp
 
 GPU_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_gravity_gpu")
+GPU_HARNESS_BATCHED = os.path.join(ROOT, "oracle", "_ref", "ref_gravity_gpu_batched")
 PATCH = os.path.join(ROOT, "patches", "sim_gravity_gpu.patch")
-have_harness = pytest.mark.skipif(not os.path.exists(GPU_HARNESS), reason="oracle/_ref/ref_gravity_gpu not built")
+PATCH_BATCHED = os.path.join(ROOT, "patches", "sim_gravity_gpu_batched.patch")
+have_harness = pytest.mark.skipif(not (os.path.exists(GPU_HARNESS) and os.path.exists(GPU_HARNESS_BATCHED)),
+                                  reason="oracle/_ref/ref_gravity_gpu[_batched] not built")
 have_reference = pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE_DIR, "sim_gravity.c")),
                                     reason="/root/reference is not mounted here")
 
@@ -38,9 +41,10 @@ def test_ed_script_applicator():
         arp.apply_ed_script(list(lines), ["12d\n"])
 
 
-def test_patch_is_an_ed_script_of_new_text_only():
+@pytest.mark.parametrize("patch", [PATCH, PATCH_BATCHED])
+def test_patch_is_an_ed_script_of_new_text_only(patch):
     """The patch names the reference's lines by number and carries only new text."""
-    text = open(PATCH).read()
+    text = open(patch).read()
     assert "gravity_cuda_step_objects" in text and "gravity_cuda_create" in text and "gravity_cuda_destroy" in text
     assert "max_thread = 1;" in text
     ref = os.path.join(REFERENCE_DIR, "sim_gravity.c")
@@ -69,6 +73,13 @@ def test_patch_applies_to_the_surveyed_revision_only(tmp_path):
     with pytest.raises(SystemExit):                  # never writes reference source into the repository
         arp.main(["x", os.path.join(REFERENCE_DIR, "sim_gravity.c"), os.path.join(ROOT, "tests", "leak.c")])
     assert not os.path.exists(os.path.join(ROOT, "tests", "leak.c"))
+    # the batching variant: same seam, the day memory moved to file scope, the clock advanced for the batch
+    batched = tmp_path / "batched.c"
+    arp.main(["x", os.path.join(REFERENCE_DIR, "sim_gravity.c"), str(batched), "--patch", PATCH_BATCHED])
+    text = batched.read_text()
+    assert text.count("gravity_cuda_step_objects(gpu") == 1 and "gravity_steps_until_day_change(sim.sim_time, dt, last_day)" in text
+    assert text.count("static int32_t") >= 1 and "                static int32_t last_day;" not in text
+    assert "day_changed = day != last_day;" in text and "obj->PATH[path_tail%MAX_PATH].X = obj->X;" in text
 
 
 @have_harness
@@ -85,15 +96,17 @@ def test_patched_unit_reports_a_missing_gpu_through_the_reference_error_rows():
 
 @pytest.mark.gpu
 @have_harness
+@pytest.mark.parametrize("harness", [GPU_HARNESS, GPU_HARNESS_BATCHED], ids=["step_by_step", "batched"])
 @pytest.mark.parametrize("name", ok_fixture_names())
-def test_patched_reference_unit_reproduces_the_goldens_on_the_gpu(name, tmp_path):
+def test_patched_reference_unit_reproduces_the_goldens_on_the_gpu(name, harness, tmp_path):
     """All six reference scenarios and the authored ones, every checkpoint (10^5 steps of the
     rogue-star scenario, 10^4 daily steps of the solar system): body state, sim_time, the number
-    of PATH samples and the digest of the reference's own PATH rings."""
+    of PATH samples and the digest of the reference's own PATH rings.  Both patches: one shim call
+    per step, and whole batches per call (up to the next commit that takes a PATH sample)."""
     fx = load_fixture(name)
     steps = [c["steps"] for c in fx["checkpoints"]]
     path = scenario_file_for(fx, tmp_path)
-    p = subprocess.run([GPU_HARNESS, path] + [str(s) for s in steps], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+    p = subprocess.run([harness, path] + [str(s) for s in steps], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600)
     assert p.returncode == 0, (p.stdout[-500:], p.stderr[-500:])
     lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
@@ -105,3 +118,9 @@ def test_patched_reference_unit_reproduces_the_goldens_on_the_gpu(name, tmp_path
         for key in ("x", "y", "vx", "vy"):
             got = [float.fromhex(b[key]) for b in l["bodies"]]
             assert bits_equal(got, cp[key + "_f"]), "%s step %d %s" % (name, l["steps"], key)
+    last, final = lines[-1], fx["checkpoints"][-1]
+    if harness == GPU_HARNESS:
+        assert last["shim_calls"] == final["steps"]
+    elif fx["dt"] > 0:
+        # one call per requested checkpoint and per PATH sample at most (+1 for a batch cut by the limit)
+        assert last["shim_calls"] <= len(steps) + final["path_tail"] + 1, (name, last["shim_calls"])
