@@ -13,8 +13,8 @@
  *
  * usage: gravity_headless (--scenario FILE | --plummer N [--seed S] | --resume SNAPSHOT)
  *            [--steps K] [--dt SECONDS] [--gpus P] [--kernel auto|tiled|strict]
- *            [--checkpoint K1,K2,...] [--save SNAPSHOT] [--save-scenario FILE]
- *            [--path-batch ROWS] [--no-path] [--quiet]
+ *            [--exchange nccl|peer] [--checkpoint K1,K2,...] [--save SNAPSHOT]
+ *            [--save-scenario FILE] [--path-batch ROWS] [--no-path] [--quiet]
  * prints one JSON line per checkpoint (body state as C99 hex floats) and a
  * final timing line.  --save-scenario writes the final state in the reference's
  * own scenario format (at most 200 bodies), readable by the original app.
@@ -76,8 +76,8 @@ static int usage(const char *argv0)
 {
     fprintf(stderr,
             "usage: %s (--scenario FILE | --plummer N [--seed S] | --resume SNAPSHOT) [--steps K] [--dt SEC]\n"
-            "          [--gpus P] [--kernel auto|tiled|strict] [--checkpoint K1,K2,...] [--save SNAPSHOT]\n"
-            "          [--save-scenario FILE] [--path-batch ROWS] [--no-path] [--quiet]\n",
+            "          [--gpus P] [--kernel auto|tiled|strict] [--exchange nccl|peer] [--checkpoint K1,K2,...]\n"
+            "          [--save SNAPSHOT] [--save-scenario FILE] [--path-batch ROWS] [--no-path] [--quiet]\n",
             argv0);
     return 2;
 }
@@ -85,7 +85,7 @@ static int usage(const char *argv0)
 int main(int argc, char **argv)
 {
     const char *scenario_file = NULL, *checkpoints = NULL, *kernel = "auto", *resume_file = NULL, *save_file = NULL;
-    const char *save_scenario_file = NULL;
+    const char *save_scenario_file = NULL, *exchange = NULL;
     long long plummer_n = 0, steps = 1000, seed = 1, done = 0, next_cp, path_batch = 4096, path_reads = 0;
     double *ring_x = NULL, *ring_y = NULL;
     int dt_override = 0, gpus = 1, quiet = 0, want_path = 1, a, i;
@@ -105,6 +105,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--dt") && a + 1 < argc) dt_override = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--gpus") && a + 1 < argc) gpus = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--kernel") && a + 1 < argc) kernel = argv[++a];
+        else if (!strcmp(argv[a], "--exchange") && a + 1 < argc) exchange = argv[++a];
         else if (!strcmp(argv[a], "--checkpoint") && a + 1 < argc) checkpoints = argv[++a];
         else if (!strcmp(argv[a], "--resume") && a + 1 < argc) resume_file = argv[++a];
         else if (!strcmp(argv[a], "--save") && a + 1 < argc) save_file = argv[++a];
@@ -189,6 +190,15 @@ int main(int argc, char **argv)
     if (strcmp(kernel, "auto") != 0) {
         if (gravity_cuda_set_option(h, "kernel", !strcmp(kernel, "tiled") ? GRAVITY_CUDA_KERNEL_TILED
                                                                            : GRAVITY_CUDA_KERNEL_STRICT) != 0) {
+            fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
+            return 1;
+        }
+    }
+    if (exchange != NULL) {
+        /* how the GPUs hand each other the new positions (barrier B2 + the commit copy): an NCCL
+         * all-gather per step, or stores into the peers' memory fused into the step kernel */
+        if (strcmp(exchange, "nccl") != 0 && strcmp(exchange, "peer") != 0) return usage(argv[0]);
+        if (gravity_cuda_set_option(h, "exchange", !strcmp(exchange, "peer")) != 0) {
             fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
             return 1;
         }
