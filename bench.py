@@ -466,7 +466,8 @@ def run_ours(args, rank, world, local_rank, ranks=None):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(n),
-            "variant": {"parallelism": "i-sharded x%d, %s" % (world, "peer-memory stores of the new positions from the step "
+            "variant": {"parallelism": "one GPU, no exchange" if world == 1 else
+                                       "i-sharded x%d, %s" % (world, "peer-memory stores of the new positions from the step "
                                        "kernel + step flags" if exchange == 1 else
                                        "NCCL all-gather of positions per step"),
                         "kernel": "tiled rsqrt, general masses, 13 FP64-pipe instr/pair" if not args.mass_fold else
