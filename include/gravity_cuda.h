@@ -76,11 +76,11 @@ int gravity_cuda_create_rank(gravity_cuda_t **out, int64_t n, int rank, int nran
                              int device, const void *nccl_id, size_t id_bytes);
 
 /* Peer-memory exchange (option "exchange" = 1).  Instead of an NCCL all-gather,
- * the step kernel stores each new position, as soon as its i-block is finished,
- * straight into every peer's copy of the next position buffer over NVLink and
- * publishes a step flag when the shard is done; the next step's kernel fetches
- * its own shard's j-tiles first and waits for the flags only when it reaches
- * other ranks' tiles.  Barrier B2 and the commit copy of the reference
+ * the step kernel stores each new position, as soon as it is committed, straight
+ * into every peer's copy of the next position buffer over NVLink and publishes
+ * its step number when the shard is done; in the next step (the same launch: a
+ * batch of steps is one launch per GPU) every CTA fetches its own shard's
+ * j-tiles first and waits for the flags only when it reaches other ranks' tiles.  Barrier B2 and the commit copy of the reference
  * (sim_gravity.c:1226, :1242-1245) thus cost no launch and overlap the math.
  * A single-process handle connects itself when the option is set.  Rank-mode
  * handles exchange one GRAVITY_CUDA_P2P_BLOB_BYTES blob per rank through the
@@ -122,6 +122,8 @@ const char *gravity_cuda_last_error(const gravity_cuda_t *h);
  * later call fails.  Raise the limit when a rank may legitimately stall longer
  * between two collective calls.
  * "trace" (0|1): record per-CTA time stamps of the tiled kernel (gravity_cuda_trace_read).
+ * "debug_shard_of" (1..8, one-GPU handles only; developer aid): plan and run like rank 0
+ * of that many ranks, without peers -- only that rank's bodies are advanced.
  * Shape options must be set before the first step/accel after create. */
 int gravity_cuda_set_option(gravity_cuda_t *h, const char *key, int64_t value);
 
