@@ -289,7 +289,9 @@ void choose_shape(int64_t n_local, int n_tile, int num_sms, int opt_threads, int
             const double useful = (double)n_local / (double)(((n_local + ib - 1) / ib) * ib);
             const double score = sh.rate * useful * per / std::ceil(per) *
                                  std::min(1.0, (double)C * sh.threads / (num_sms * 256.0));
-            if (score > best) {
+            // the shapes are listed biggest first; a smaller one has to promise more than 1 % to win
+            // (at a tie the bigger i-block is the faster one in practice: N = 6,144, tools/explore.py)
+            if (best < 0.0 || score > best * 1.01) {
                 best = score;
                 threads = sh.threads;
                 bpt = sh.bpt;
