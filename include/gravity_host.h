@@ -89,13 +89,28 @@ int gravity_plummer_generate(int64_t n, uint64_t seed, double *mass, double *x, 
  * reference has neither; its state lives only in RAM and re-selecting a scenario
  * restarts from sim_time = 0, sim_gravity.c:415).  Layout, little endian:
  * char magic[8] = "GRAVSNP1"; int64 n; int64 sim_time; int32 dt; int32 last_day;
- * then mass, x, y, vx, vy as n doubles each.  read() allocates one block that
+ * then mass, x, y, vx, vy as n doubles each (write() now emits version 2 with no samples,
+ * see below; read() takes either).  read() allocates one block that
  * the caller frees through *mass (x, y, vx, vy point into it). */
 int gravity_snapshot_write(const char *pathname, int64_t n, int64_t sim_time, int32_t dt, int32_t last_day,
                            const double *mass, const double *x, const double *y,
                            const double *vx, const double *vy);
 int gravity_snapshot_read(const char *pathname, int64_t *n, int64_t *sim_time, int32_t *dt, int32_t *last_day,
                           double **mass, double **x, double **y, double **vx, double **vy);
+
+/* The same with the PATH rings (sim_gravity.c:101-104, :1248-1260), so that a resumed run
+ * continues them: magic "GRAVSNP2", the v1 header followed by int64 path_tail (samples taken
+ * so far) and int64 path_count (samples stored: the most recent ones, oldest first), the five
+ * columns, then path_count rows of n {X,Y} pairs.  read_path() accepts both versions (a v1
+ * file has no samples); *path_xy is a separate block the caller frees (NULL when empty);
+ * the three path pointers may be NULL. */
+int gravity_snapshot_write_path(const char *pathname, int64_t n, int64_t sim_time, int32_t dt, int32_t last_day,
+                                const double *mass, const double *x, const double *y,
+                                const double *vx, const double *vy,
+                                int64_t path_tail, int64_t path_count, const double *path_xy);
+int gravity_snapshot_read_path(const char *pathname, int64_t *n, int64_t *sim_time, int32_t *dt, int32_t *last_day,
+                               double **mass, double **x, double **y, double **vx, double **vy,
+                               int64_t *path_tail, int64_t *path_count, double **path_xy);
 
 /* How many steps of size dt may run from sim_time before the reference would
  * take its next PATH sample: the commit at sim_gravity.c:1232-1236 samples the

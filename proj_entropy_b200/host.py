@@ -47,6 +47,13 @@ def load_host_library():
         "gravity_steps_until_day_change": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
         "gravity_snapshot_write": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                              _dp, _dp, _dp, _dp, _dp]),
+        "gravity_snapshot_write_path": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                                  _dp, _dp, _dp, _dp, _dp, C.c_int64, C.c_int64, _dp]),
+        "gravity_snapshot_read_path": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                 C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp),
+                                                 C.POINTER(_dp), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                                 C.POINTER(_dp)]),
         "gravity_snapshot_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                             C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp),
@@ -128,25 +135,41 @@ def steps_until_day_change(sim_time, dt, last_day):
     return load_host_library().gravity_steps_until_day_change(int(sim_time), int(dt), int(last_day))
 
 
-def snapshot_write(pathname, sim_time, dt, last_day, mass, x, y, vx, vy):
+def snapshot_write(pathname, sim_time, dt, last_day, mass, x, y, vx, vy, path_tail=0, path_xy=None):
+    """path_xy: the most recent PATH samples, oldest first, shape [samples, n, 2] (optional)."""
     lib = load_host_library()
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (mass, x, y, vx, vy)]
-    if lib.gravity_snapshot_write(os.fsencode(pathname), len(arrs[0]), int(sim_time), int(dt), int(last_day),
-                                  *[a.ctypes.data_as(_dp) for a in arrs]) != 0:
+    n = len(arrs[0])
+    if path_xy is None:
+        rc = lib.gravity_snapshot_write(os.fsencode(pathname), n, int(sim_time), int(dt), int(last_day),
+                                        *[a.ctypes.data_as(_dp) for a in arrs])
+    else:
+        p = np.ascontiguousarray(path_xy, dtype=np.float64).reshape(-1, n, 2)
+        rc = lib.gravity_snapshot_write_path(os.fsencode(pathname), n, int(sim_time), int(dt), int(last_day),
+                                             *[a.ctypes.data_as(_dp) for a in arrs], int(path_tail), len(p),
+                                             p.ctypes.data_as(_dp))
+    if rc != 0:
         raise OSError("cannot write snapshot %s" % pathname)
 
 
 def snapshot_read(pathname):
-    """-> dict(n, sim_time, dt, last_day, mass, x, y, vx, vy)"""
+    """-> dict(n, sim_time, dt, last_day, mass, x, y, vx, vy, path_tail, path_xy [samples, n, 2])"""
     lib = load_host_library()
     n, t, dt, ld = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+    tail, count, path = C.c_int64(), C.c_int64(), _dp()
     ptrs = [_dp() for _ in range(5)]
-    if lib.gravity_snapshot_read(os.fsencode(pathname), C.byref(n), C.byref(t), C.byref(dt), C.byref(ld),
-                                 *[C.byref(p) for p in ptrs]) != 0:
+    if lib.gravity_snapshot_read_path(os.fsencode(pathname), C.byref(n), C.byref(t), C.byref(dt), C.byref(ld),
+                                      *[C.byref(p) for p in ptrs], C.byref(tail), C.byref(count), C.byref(path)) != 0:
         raise OSError("cannot read snapshot %s" % pathname)
+    libc = C.CDLL(None)
     try:
         cols = [np.ctypeslib.as_array(p, shape=(n.value,)).copy() for p in ptrs]
+        pxy = np.zeros((0, n.value, 2))
+        if count.value > 0:
+            pxy = np.ctypeslib.as_array(path, shape=(count.value, n.value, 2)).copy()
     finally:
-        C.CDLL(None).free(C.cast(ptrs[0], C.c_void_p))
+        libc.free(C.cast(ptrs[0], C.c_void_p))
+        if path:
+            libc.free(C.cast(path, C.c_void_p))
     return dict(n=n.value, sim_time=t.value, dt=dt.value, last_day=ld.value, mass=cols[0], x=cols[1], y=cols[2],
-                vx=cols[3], vy=cols[4])
+                vx=cols[3], vy=cols[4], path_tail=tail.value, path_xy=pxy)

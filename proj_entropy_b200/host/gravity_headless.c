@@ -87,12 +87,13 @@ int main(int argc, char **argv)
     const char *scenario_file = NULL, *checkpoints = NULL, *kernel = "auto", *resume_file = NULL, *save_file = NULL;
     const char *save_scenario_file = NULL, *exchange = NULL;
     long long plummer_n = 0, steps = 1000, seed = 1, done = 0, next_cp, path_batch = 4096, path_reads = 0;
-    double *ring_x = NULL, *ring_y = NULL;
+    double *ring_x = NULL, *ring_y = NULL, *resume_path = NULL;
+    int64_t resume_tail = 0, resume_count = 0;
     int dt_override = 0, gpus = 1, quiet = 0, want_path = 1, a, i;
     gravity_scenario_t *sim = NULL;
     gravity_cuda_t *h = NULL;
     path_point_t *path = NULL;
-    long long path_tail = 0;
+    long long path_tail = 0, device_tail = 0;
     int32_t last_day = 0; /* function-static in the reference, starts at 0 */
     uint64_t t0, t1;
     char *cp_cursor = NULL;
@@ -129,7 +130,8 @@ int main(int argc, char **argv)
         int64_t rn = 0, rt = 0;
         int32_t rdt = 0, rld = 0;
         double *m, *x, *y, *vx, *vy;
-        if (gravity_snapshot_read(resume_file, &rn, &rt, &rdt, &rld, &m, &x, &y, &vx, &vy) != 0) {
+        if (gravity_snapshot_read_path(resume_file, &rn, &rt, &rdt, &rld, &m, &x, &y, &vx, &vy, &resume_tail,
+                                       &resume_count, &resume_path) != 0) {
             fprintf(stderr, "ERROR cannot read snapshot '%s'\n", resume_file);
             return 1;
         }
@@ -217,7 +219,20 @@ int main(int argc, char **argv)
             fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
             return 1;
         }
+        if (resume_path != NULL) {
+            /* the PATH rings as they were when the snapshot was taken: the run continues them */
+            long long k;
+            for (k = 0; k < resume_count; k++) {
+                const size_t slot = (size_t)((resume_tail - resume_count + k) % MAX_PATH_SAMPLES);
+                for (i = 0; i < sim->n; i++) {
+                    path[(size_t)i * MAX_PATH_SAMPLES + slot].x = resume_path[((size_t)k * sim->n + i) * 2];
+                    path[(size_t)i * MAX_PATH_SAMPLES + slot].y = resume_path[((size_t)k * sim->n + i) * 2 + 1];
+                }
+            }
+            path_tail = resume_tail;
+        }
     }
+    free(resume_path);
 
     if (checkpoints) cp_cursor = strdup(checkpoints);
     next_cp = -1;
@@ -243,15 +258,16 @@ int main(int argc, char **argv)
             if (sim->dt < 86400) cap_steps = (path_batch - 2) * (86400 / sim->dt);
             long long tail_after = 0;
             long long k;
+            const long long tail_base = path_tail - device_tail;    /* samples taken before this process */
             if (batch > cap_steps) batch = cap_steps;
             if (gravity_cuda_step_path(h, sim->dt, batch, sim->sim_time, &last_day, (int64_t *)&tail_after) != 0) {
                 fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
                 return 1;
             }
             /* the commit block's PATH writes (sim_gravity.c:1248-1251, :1258-1260), fetched once per batch */
-            if (tail_after > path_tail) {
-                const long long cnt = tail_after - path_tail;
-                if (gravity_cuda_path_read(h, path_tail, cnt, ring_x, ring_y) != 0) {
+            if (tail_after > device_tail) {
+                const long long cnt = tail_after - device_tail;
+                if (gravity_cuda_path_read(h, device_tail, cnt, ring_x, ring_y) != 0) {
                     fprintf(stderr, "ERROR %s\n", gravity_cuda_last_error(h));
                     return 1;
                 }
@@ -263,7 +279,8 @@ int main(int argc, char **argv)
                         path[(size_t)i * MAX_PATH_SAMPLES + slot].y = ring_y[(size_t)k * sim->n + i];
                     }
                 }
-                path_tail = tail_after;
+                device_tail = tail_after;
+                path_tail = tail_base + device_tail;
             }
         } else {
             if (gravity_cuda_step(h, sim->dt, batch) != 0) {
@@ -286,12 +303,24 @@ int main(int argc, char **argv)
     t1 = microsec_now();
 
     if (save_file) {
+        /* state, clock, the day memory and -- so that a resumed run continues them -- the PATH rings */
+        const long long stored = path ? (path_tail < MAX_PATH_SAMPLES ? path_tail : MAX_PATH_SAMPLES) : 0;
+        double *rings = stored > 0 ? malloc(sizeof(double) * 2 * (size_t)stored * (size_t)sim->n) : NULL;
+        long long k;
+        for (k = 0; rings != NULL && k < stored; k++) {
+            const size_t slot = (size_t)((path_tail - stored + k) % MAX_PATH_SAMPLES);
+            for (i = 0; i < sim->n; i++) {
+                rings[((size_t)k * sim->n + i) * 2] = path[(size_t)i * MAX_PATH_SAMPLES + slot].x;
+                rings[((size_t)k * sim->n + i) * 2 + 1] = path[(size_t)i * MAX_PATH_SAMPLES + slot].y;
+            }
+        }
         if (gravity_cuda_download(h, sim->x, sim->y, sim->vx, sim->vy) != 0 ||
-            gravity_snapshot_write(save_file, sim->n, sim->sim_time, sim->dt, last_day, sim->mass, sim->x, sim->y,
-                                   sim->vx, sim->vy) != 0) {
+            gravity_snapshot_write_path(save_file, sim->n, sim->sim_time, sim->dt, last_day, sim->mass, sim->x, sim->y,
+                                        sim->vx, sim->vy, rings ? path_tail : 0, rings ? stored : 0, rings) != 0) {
             fprintf(stderr, "ERROR cannot write snapshot '%s'\n", save_file);
             return 1;
         }
+        free(rings);
     }
     if (save_scenario_file) {
         int rc;

@@ -362,51 +362,80 @@ int64_t gravity_steps_until_day_change(int64_t sim_time, int32_t dt, int32_t las
 
 /* ---- binary snapshots ----------------------------------------------------------- */
 
-static const char k_snap_magic[8] = {'G', 'R', 'A', 'V', 'S', 'N', 'P', '1'};
+static const char k_snap_magic1[8] = {'G', 'R', 'A', 'V', 'S', 'N', 'P', '1'};
+static const char k_snap_magic2[8] = {'G', 'R', 'A', 'V', 'S', 'N', 'P', '2'};
 
-int gravity_snapshot_write(const char *pathname, int64_t n, int64_t sim_time, int32_t dt, int32_t last_day,
-                           const double *mass, const double *x, const double *y,
-                           const double *vx, const double *vy)
+int gravity_snapshot_write_path(const char *pathname, int64_t n, int64_t sim_time, int32_t dt, int32_t last_day,
+                                const double *mass, const double *x, const double *y,
+                                const double *vx, const double *vy,
+                                int64_t path_tail, int64_t path_count, const double *path_xy)
 {
     const double *cols[5] = {mass, x, y, vx, vy};
     FILE *fp;
     int c, ok = 1;
     if (!pathname || n < 1 || !mass || !x || !y || !vx || !vy) return -1;
+    if (path_count < 0 || path_tail < path_count || (path_count > 0 && !path_xy)) return -1;
     fp = fopen(pathname, "wb");
     if (fp == NULL) return -1;
-    ok &= fwrite(k_snap_magic, 1, 8, fp) == 8;
+    ok &= fwrite(k_snap_magic2, 1, 8, fp) == 8;
     ok &= fwrite(&n, sizeof(n), 1, fp) == 1;
     ok &= fwrite(&sim_time, sizeof(sim_time), 1, fp) == 1;
     ok &= fwrite(&dt, sizeof(dt), 1, fp) == 1;
     ok &= fwrite(&last_day, sizeof(last_day), 1, fp) == 1;
+    ok &= fwrite(&path_tail, sizeof(path_tail), 1, fp) == 1;
+    ok &= fwrite(&path_count, sizeof(path_count), 1, fp) == 1;
     for (c = 0; c < 5 && ok; c++) ok &= fwrite(cols[c], sizeof(double), (size_t)n, fp) == (size_t)n;
+    if (ok && path_count > 0) {
+        const size_t cnt = (size_t)path_count * (size_t)n * 2;
+        ok &= fwrite(path_xy, sizeof(double), cnt, fp) == cnt;
+    }
     ok &= fclose(fp) == 0;
     return ok ? 0 : -1;
 }
 
-int gravity_snapshot_read(const char *pathname, int64_t *n, int64_t *sim_time, int32_t *dt, int32_t *last_day,
-                          double **mass, double **x, double **y, double **vx, double **vy)
+int gravity_snapshot_write(const char *pathname, int64_t n, int64_t sim_time, int32_t dt, int32_t last_day,
+                           const double *mass, const double *x, const double *y,
+                           const double *vx, const double *vy)
+{
+    return gravity_snapshot_write_path(pathname, n, sim_time, dt, last_day, mass, x, y, vx, vy, 0, 0, NULL);
+}
+
+int gravity_snapshot_read_path(const char *pathname, int64_t *n, int64_t *sim_time, int32_t *dt, int32_t *last_day,
+                               double **mass, double **x, double **y, double **vx, double **vy,
+                               int64_t *path_tail, int64_t *path_count, double **path_xy)
 {
     char magic[8];
-    int64_t cnt = 0, t = 0;
+    int64_t cnt = 0, t = 0, tail = 0, pcount = 0;
     int32_t d = 0, ld = 0;
-    double *block;
+    double *block, *path = NULL;
     FILE *fp;
+    int v2;
     if (!pathname || !n || !sim_time || !dt || !last_day || !mass || !x || !y || !vx || !vy) return -1;
     fp = fopen(pathname, "rb");
     if (fp == NULL) return -1;
-    if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, k_snap_magic, 8) != 0 ||
-        fread(&cnt, sizeof(cnt), 1, fp) != 1 || fread(&t, sizeof(t), 1, fp) != 1 ||
+    if (fread(magic, 1, 8, fp) != 8) goto bad;
+    v2 = memcmp(magic, k_snap_magic2, 8) == 0;
+    if (!v2 && memcmp(magic, k_snap_magic1, 8) != 0) goto bad;
+    if (fread(&cnt, sizeof(cnt), 1, fp) != 1 || fread(&t, sizeof(t), 1, fp) != 1 ||
         fread(&d, sizeof(d), 1, fp) != 1 || fread(&ld, sizeof(ld), 1, fp) != 1 || cnt < 1 ||
-        cnt > ((int64_t)1 << 40)) {
-        fclose(fp);
-        return -1;
-    }
+        cnt > ((int64_t)1 << 40))
+        goto bad;
+    if (v2 && (fread(&tail, sizeof(tail), 1, fp) != 1 || fread(&pcount, sizeof(pcount), 1, fp) != 1 || pcount < 0 ||
+               tail < pcount || pcount > ((int64_t)1 << 32) / cnt))
+        goto bad;
     block = malloc(sizeof(double) * 5 * (size_t)cnt);
     if (block == NULL || fread(block, sizeof(double), 5 * (size_t)cnt, fp) != 5 * (size_t)cnt) {
         free(block);
-        fclose(fp);
-        return -1;
+        goto bad;
+    }
+    if (pcount > 0 && path_xy != NULL) {
+        const size_t words = (size_t)pcount * (size_t)cnt * 2;
+        path = malloc(sizeof(double) * words);
+        if (path == NULL || fread(path, sizeof(double), words, fp) != words) {
+            free(path);
+            free(block);
+            goto bad;
+        }
     }
     fclose(fp);
     *n = cnt;
@@ -418,7 +447,19 @@ int gravity_snapshot_read(const char *pathname, int64_t *n, int64_t *sim_time, i
     *y = block + 2 * cnt;
     *vx = block + 3 * cnt;
     *vy = block + 4 * cnt;
+    if (path_tail) *path_tail = tail;
+    if (path_count) *path_count = path ? pcount : 0;
+    if (path_xy) *path_xy = path;
     return 0;
+bad:
+    fclose(fp);
+    return -1;
+}
+
+int gravity_snapshot_read(const char *pathname, int64_t *n, int64_t *sim_time, int32_t *dt, int32_t *last_day,
+                          double **mass, double **x, double **y, double **vx, double **vy)
+{
+    return gravity_snapshot_read_path(pathname, n, sim_time, dt, last_day, mass, x, y, vx, vy, NULL, NULL, NULL);
 }
 
 /* ---- Plummer model ----------------------------------------------------------- */

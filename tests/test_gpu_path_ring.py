@@ -159,3 +159,26 @@ def test_headless_daily_steps_need_no_download_per_day():
     assert summary["kernel_launches"] < 40                             # not one launch per step
     for key in ("x", "y", "vx", "vy"):
         assert bits_equal([float.fromhex(b[key]) for b in state["bodies"]], cp[key + "_f"]), key
+
+
+def test_headless_resume_continues_the_path_rings(tmp_path):
+    """2,000 daily steps straight, and 1,200 + a snapshot + 800 in a new process: the same PATH rings
+    (count and digest -- the snapshot carries the samples taken so far), the same state, the same clock."""
+    exe = os.path.join(ROOT, "proj_entropy_b200", "gravity_headless")
+    scen = os.path.join(ROOT, "tests", "golden", "scenarios", "solar_system_daily")
+    snap = str(tmp_path / "mid.snap")
+
+    def run(*args):
+        p = subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert p.returncode == 0, p.stderr
+        return [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+
+    straight = run("--scenario", scen, "--steps", "2000", "--checkpoint", "2000", "--path-batch", "512")
+    first = run("--scenario", scen, "--steps", "1200", "--path-batch", "512", "--save", snap)
+    resumed = run("--resume", snap, "--steps", "800", "--checkpoint", "800", "--path-batch", "300")
+    assert first[-1]["path_samples"] == 1199
+    a, b = straight[-1], resumed[-1]
+    assert a["path_samples"] == b["path_samples"] == 1999 and a["path_hash"] == b["path_hash"]
+    assert a["sim_time"] == b["sim_time"] and a["last_day"] == b["last_day"]
+    for key in ("x", "y", "vx", "vy"):
+        assert [q[key] for q in straight[0]["bodies"]] == [q[key] for q in resumed[0]["bodies"]]

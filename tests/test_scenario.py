@@ -106,11 +106,37 @@ def test_snapshot_round_trip(tmp_path):
     assert (s["n"], s["sim_time"], s["dt"], s["last_day"]) == (1234, 86399, 7, 0)
     for a, b in zip((m, x, y, vx, vy), (s["mass"], s["x"], s["y"], s["vx"], s["vy"])):
         assert bits_equal(a, b)
-    assert os.path.getsize(p) == 8 + 8 + 8 + 4 + 4 + 5 * 8 * 1234
+    assert os.path.getsize(p) == 8 + 8 + 8 + 4 + 4 + 8 + 8 + 5 * 8 * 1234 and s["path_tail"] == 0 and len(s["path_xy"]) == 0
     bad = tmp_path / "bad.bin"
     bad.write_bytes(b"NOTASNAP" + bytes(64))
     with pytest.raises(OSError):
         g.snapshot_read(str(bad))
+    # version 1 files (no PATH section) are still read
+    import struct
+    v1 = tmp_path / "v1.bin"
+    v1.write_bytes(b"GRAVSNP1" + struct.pack("<qqii", 3, 500, 60, 2) + np.arange(15, dtype=np.float64).tobytes())
+    s = g.snapshot_read(str(v1))
+    assert (s["n"], s["sim_time"], s["dt"], s["last_day"], s["path_tail"]) == (3, 500, 60, 2, 0)
+    assert s["mass"].tolist() == [0.0, 1.0, 2.0] and s["vy"].tolist() == [12.0, 13.0, 14.0]
+
+
+def test_snapshot_carries_the_path_rings(tmp_path):
+    """Version 2: the samples taken so far and the most recent ones, oldest first, so that a resumed run
+    continues the PATH rings (sim_gravity.c:1248-1260); truncated and inconsistent files are refused."""
+    n = 7
+    m, x, y, vx, vy = g.plummer(n, seed=5)
+    rings = np.random.default_rng(1).normal(size=(40, n, 2))
+    p = tmp_path / "snap2.bin"
+    g.snapshot_write(str(p), 86400 * 123, 86400, 122, m, x, y, vx, vy, path_tail=100040, path_xy=rings)
+    s = g.snapshot_read(str(p))
+    assert (s["n"], s["sim_time"], s["dt"], s["last_day"], s["path_tail"]) == (n, 86400 * 123, 86400, 122, 100040)
+    assert bits_equal(s["path_xy"], rings) and bits_equal(s["x"], x)
+    raw = p.read_bytes()
+    (tmp_path / "cut.bin").write_bytes(raw[:-8])
+    with pytest.raises(OSError):
+        g.snapshot_read(str(tmp_path / "cut.bin"))
+    with pytest.raises(OSError):                       # more samples stored than ever taken
+        g.snapshot_write(str(tmp_path / "no.bin"), 0, 1, 0, m, x, y, vx, vy, path_tail=3, path_xy=rings)
 
 
 def test_out_of_range_dt_behaves_like_the_reference_build(tmp_path):
